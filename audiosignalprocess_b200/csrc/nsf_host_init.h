@@ -1,0 +1,113 @@
+// Host-side construction of the float-NS constant tables and of a freshly
+// initialised per-stream state slab (the job of WebRtcNs_InitCore,
+// ns_core.c:74-214, and WebRtcNs_set_policy_core, ns_core.c:1013-1041).
+// Plain C++; no CUDA calls.  Used by the C-ABI host layer (ns_capi.cu) and by
+// the test-only SIMT emulator.
+#ifndef AUDIOSIGNALPROCESS_B200_NSF_HOST_INIT_H_
+#define AUDIOSIGNALPROCESS_B200_NSF_HOST_INIT_H_
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "nsf_layout.h"
+
+namespace nsb200 {
+
+// Hybrid Hann/flat window (windows_private.h:64,94): a sine rise over the
+// overlap, flat top, mirrored fall.  The reference tabulates it to 8 decimals;
+// rounding sin() to 8 decimals in double and then to float reproduces the
+// table bit for bit (checked in tests/test_tables.py against the reference).
+inline void nsf_make_window(int ana, float* w) {
+  const int rise = ana == 256 ? 96 : 48;
+  const double kPi = 3.14159265358979323846;
+  for (int i = 0; i < ana; ++i) {
+    double v;
+    if (i < rise) v = sin(kPi * i / (2.0 * rise));
+    else if (i <= ana - rise) v = 1.0;
+    else v = sin(kPi * (ana - i) / (2.0 * rise));
+    w[i] = (float)(floor(v * 1e8 + 0.5) / 1e8);
+  }
+}
+
+template <typename Tables>
+inline void nsf_fill_tables(Tables* t) {
+  memset(t, 0, sizeof(*t));
+  nsf_make_window(256, t->win256);
+  nsf_make_window(128, t->win128);
+  const double kPi = 3.14159265358979323846;
+  for (int k = 0; k < 256; ++k) {
+    t->tw[k].x = (float)cos(2.0 * kPi * k / 256.0);
+    t->tw[k].y = (float)sin(2.0 * kPi * k / 256.0);
+  }
+  t->tw[0].x = 1.f;   t->tw[0].y = 0.f;
+  t->tw[64].x = 0.f;  t->tw[64].y = 1.f;
+  t->tw[128].x = -1.f; t->tw[128].y = 0.f;
+  t->tw[192].x = 0.f; t->tw[192].y = -1.f;
+  for (int i = 1; i < 132; ++i) t->logi[i] = (float)log((double)(float)i);
+  // sequential float sums exactly as ns_core.c:1088-1100 accumulates them
+  for (int v = 0; v < 2; ++v) {
+    const int magn_len = v == 0 ? 129 : 65;
+    float s = 0.f, s2 = 0.f;
+    for (int i = 5; i < magn_len; ++i) {
+      const float l = t->logi[i];
+      s += l;
+      s2 += l * l;
+    }
+    t->sum_log_i[v] = s;
+    t->sum_log_i_sq[v] = s2;
+  }
+}
+
+inline bool nsf_mode_params(int mode, float* overdrive, float* denoise_bound, int* gainmap) {
+  switch (mode) {  // ns_core.c:1020-1039
+    case 0: *overdrive = 1.f;   *denoise_bound = 0.5f;   *gainmap = 0; return true;
+    case 1: *overdrive = 1.f;   *denoise_bound = 0.25f;  *gainmap = 1; return true;
+    case 2: *overdrive = 1.1f;  *denoise_bound = 0.125f; *gainmap = 1; return true;
+    case 3: *overdrive = 1.25f; *denoise_bound = 0.09f;  *gainmap = 1; return true;
+  }
+  return false;
+}
+
+inline void nsf_set_mode(uint32_t* slab, int mode) {
+  float od = 1.f, db = 0.5f;
+  int gm = 0;
+  nsf_mode_params(mode, &od, &db, &gm);
+  memcpy(slab + kH_overdrive, &od, 4);
+  memcpy(slab + kH_denoiseBound, &db, 4);
+  slab[kH_gainmap] = (uint32_t)gm;
+  slab[kH_mode] = (uint32_t)mode;
+}
+
+inline void nsf_init_state(uint32_t* slab, uint32_t fs) {
+  memset(slab, 0, sizeof(uint32_t) * (size_t)kNsfStateWords);
+  float* f = reinterpret_cast<float*>(slab);
+  int32_t* i = reinterpret_cast<int32_t*>(slab);
+  i[kH_blockInd] = -1;
+  i[kH_updates] = 0;
+  for (int s = 0; s < 3; ++s)
+    i[kH_counter + s] = (int)floor((float)(200 * (s + 1)) / 3.f);  // 66, 133, 200
+  i[kH_modelUpd0] = 2;
+  i[kH_modelUpd3] = 500;
+  const float pars[7] = {0.5f, 0.5f, 1.f, 0.5f, 1.f, 0.f, 0.f};
+  for (int k = 0; k < 7; ++k) f[kH_priorPars + k] = pars[k];
+  f[kH_priorSpeechProb] = 0.5f;
+  const float feat[7] = {0.5f, 0.f, 0.f, 0.5f, 0.5f, 0.f, 0.f};
+  for (int k = 0; k < 7; ++k) f[kH_feat + k] = feat[k];
+  i[kH_fs] = (int32_t)fs;
+  i[kH_initFlag] = 1;
+  for (int b = 0; b < 129; ++b) {
+    float* r = f + kNsfOffBins + b * kNsfBinRec;
+    for (int s = 0; s < 3; ++s) {
+      r[kB_lq0 + s] = 8.f;
+      r[kB_dens0 + s] = 0.3f;
+    }
+    r[kB_smooth] = 1.f;
+    r[kB_logLrt] = 0.5f;
+  }
+  nsf_set_mode(slab, 0);
+}
+
+}  // namespace nsb200
+
+#endif  // AUDIOSIGNALPROCESS_B200_NSF_HOST_INIT_H_

@@ -1,0 +1,825 @@
+// Float noise suppressor (WebRtcNs_Analyze + WebRtcNs_Process fused) as one
+// sm_100a kernel: one warp per stream walks F 10-ms frames; lanes own bins.
+//
+// What it replaces in the reference (webrtc/modules/audio_processing/ns/):
+//   WebRtcNs_AnalyzeCore   ns_core.c:1043-1181
+//   WebRtcNs_ProcessCore   ns_core.c:1183-1415
+//   and everything they call: UpdateBuffer :855, Windowing :969, Energy :951,
+//   FFT/IFFT :886/:923 (Ooura rdft, utility/fft4g.c:324), NoiseEstimation :217,
+//   ComputeSnr :566, ComputeSpectralFlatness :523, ComputeSpectralDifference
+//   :595, FeatureUpdate :755, FeatureParameterExtraction :293, SpeechNoiseProb
+//   :642, UpdateNoiseEstimate :800, ComputeDdBasedWienerFilter :985.
+// All three reference call sites feed Analyze and Process the same frame
+// (test_ns_module.cpp:97-99, libapm/src/apm_ns.cpp:69-74), so analyzeBuf ==
+// dataBuf and magnPrevAnalyze == magnPrevProcess: one forward FFT per frame.
+//
+// Data layout
+//   HBM  per-stream state slab of kNsfStateWords 32-bit words (SoA inside the
+//        slab: header scalars | analysis history | synthesis overlap | HB
+//        delay lines | initMagnEst | per-bin records of 12 floats), plus a
+//        cold slab of 3x1000 histogram counters per stream.
+//   SMEM per warp: header, per-bin records, FFT scratch. Per CTA: window,
+//        twiddles, log(i) table.
+//   REGS analysis history / synthesis overlap (pairs of samples per lane).
+#ifndef AUDIOSIGNALPROCESS_B200_NSF_KERNEL_CUH_
+#define AUDIOSIGNALPROCESS_B200_NSF_KERNEL_CUH_
+
+#include "ns_warp.cuh"
+#include "nsf_layout.h"
+
+namespace nsb200 {
+
+constexpr int kNsfWarpsPerCta = 4;
+constexpr int kNsfCtaTableWords = 912;  // win 256 | tw 512 | logi 132 | pad
+constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
+
+template <int ANA>
+struct NsfGeo {
+  static constexpr int kFrame = ANA == 256 ? 160 : 80;
+  static constexpr int kBins = ANA / 2 + 1;
+  static constexpr int kNC = ANA / 2;           // complex points
+  static constexpr int kL = kNC / 4;            // FFT lanes
+  static constexpr int kSlots = kNC / 32 + 1;   // bins per lane incl. Nyquist slot
+  static constexpr int kFP = kFrame / 2;        // frame sample pairs (80 / 40)
+  static constexpr int kHP = (ANA - kFrame) / 2;  // history pairs (48 / 24)
+  static constexpr int kTP = ANA / 2;           // all pairs
+};
+
+NSB_DEV int pad_idx(int k) { return k + ((k >> 6) << 1); }
+
+NSB_DEV float sat_s16f(float v) {  // WEBRTC_SPL_SAT(32767, v, -32768)
+  return v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v);
+}
+NSB_DEV int round_s16(float v) {  // FloatS16ToS16, common_audio/include/audio_util.h:41-49
+  if (v > 0.f) return v >= 32766.5f ? 32767 : (int)(v + 0.5f);
+  return v <= -32767.5f ? -32768 : (int)(v - 0.5f);
+}
+
+// ---- threshold re-estimation every 500 frames (ns_core.c:337-517), warp parallel.
+// Peak search semantics of the sequential scan (strict '>' both times):
+//   peak1 = first occurrence of the maximum;
+//   peak2 = first occurrence of the maximum over all other bins, if > 0.
+NSB_DEV void nsf_hist_two_peaks(const int* h, int lane, int& w1, int& i1, int& w2, int& i2) {
+  int bv = 0, bi = 0x7fffffff;
+  for (int i = lane; i < 1000; i += 32) {
+    const int v = __ldcg(h + i);
+    if (v > bv) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ov = __shfl_xor_sync(kFullMask, bv, o), oi = __shfl_xor_sync(kFullMask, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  w1 = bv; i1 = bi;
+  int cv = 0, ci = 0x7fffffff;
+  for (int i = lane; i < 1000; i += 32) {
+    const int v = __ldcg(h + i);
+    if (i != i1 && v > cv) { cv = v; ci = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ov = __shfl_xor_sync(kFullMask, cv, o), oi = __shfl_xor_sync(kFullMask, ci, o);
+    if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; }
+  }
+  w2 = cv; i2 = ci;
+}
+
+NSB_DEV void nsf_extract_params(float* H, int* hist, int lane) {
+  int* hLrt = hist;
+  int* hFlat = hist + 1000;
+  int* hDiff = hist + 2000;
+  // LRT fluctuation.
+  float avg = 0.f, avgC = 0.f, avgSq = 0.f;
+  int num = 0;
+  for (int i = lane; i < 1000; i += 32) {
+    const int c = __ldcg(hLrt + i);  // counters are bumped by L2 atomics: bypass L1
+    const float mid = ((float)i + 0.5f) * 0.1f;
+    if (mid <= 1.f) { avg += c * mid; num += c; }
+    avgSq += c * mid * mid;
+    avgC += c * mid;
+  }
+  warp_sum3(avg, avgC, avgSq);
+  num = warp_sum_i(num);
+  if (num > 0) avg = avg / (float)num;
+  avgC = avgC / 500.f;
+  avgSq = avgSq / 500.f;
+  const float fluct = avgSq - avg * avgC;
+  float thrLrt;
+  if (fluct < 0.05f) {
+    thrLrt = 1.f;
+  } else {
+    thrLrt = 1.2f * avg;
+    if (thrLrt < 0.2f) thrLrt = 0.2f;
+    if (thrLrt > 1.f) thrLrt = 1.f;
+  }
+  H[kH_priorPars + 0] = thrLrt;
+
+  int w1, i1, w2, i2;
+  // spectral flatness: bin 0.05
+  nsf_hist_two_peaks(hFlat, lane, w1, i1, w2, i2);
+  float p1 = w1 > 0 ? ((float)i1 + 0.5f) * 0.05f : 0.f;
+  float p2 = w2 > 0 ? ((float)i2 + 0.5f) * 0.05f : 0.f;
+  int useFlat = 1;
+  if (fabsf(p2 - p1) < 2 * 0.05f && (float)w2 > 0.5f * (float)w1) {
+    w1 += w2;
+    p1 = 0.5f * (p1 + p2);
+  }
+  if (w1 < 150 || p1 < 0.6f) useFlat = 0;
+  if (useFlat) {
+    float t = 0.9f * p1;
+    if (t < 0.1f) t = 0.1f;
+    if (t > 0.95f) t = 0.95f;
+    H[kH_priorPars + 1] = t;
+  }
+  // spectral difference: bin 0.1
+  nsf_hist_two_peaks(hDiff, lane, w1, i1, w2, i2);
+  p1 = w1 > 0 ? ((float)i1 + 0.5f) * 0.1f : 0.f;
+  p2 = w2 > 0 ? ((float)i2 + 0.5f) * 0.1f : 0.f;
+  int useDiff = 1;
+  if (fabsf(p2 - p1) < 2 * 0.1f && (float)w2 > 0.5f * (float)w1) {
+    w1 += w2;
+    p1 = 0.5f * (p1 + p2);
+  }
+  float td = 1.2f * p1;
+  if (w1 < 150) useDiff = 0;
+  if (td < 0.16f) td = 0.16f;
+  if (td > 1.f) td = 1.f;
+  H[kH_priorPars + 3] = td;
+  if (fluct < 0.05f) useDiff = 0;
+  const float fsum = (float)(1 + useFlat + useDiff);
+  H[kH_priorPars + 4] = 1.f / fsum;
+  H[kH_priorPars + 5] = (float)useFlat / fsum;
+  H[kH_priorPars + 6] = (float)useDiff / fsum;
+  __syncwarp();
+  for (int i = lane; i < 3000; i += 32) hist[i] = 0;
+}
+
+// ---- the kernel -------------------------------------------------------------
+// ANA: 256 (16/32/48 kHz band 0) or 128 (8 kHz). NB: number of bands (1..3).
+// I16: PCM is int16 (rounded on output like IFChannelBuffer::RefreshI,
+// channel_buffer.cc:55-60) or float in int16 scale (the WebRtcNs_Process ABI).
+template <int ANA, int NB, bool I16>
+__global__ void __launch_bounds__(kNsfWarpsPerCta * 32)
+nsf_process_kernel(const NsfLaunch p) {
+  typedef NsfGeo<ANA> G;
+  extern __shared__ float4 nsf_smem4[];
+  float* smem = reinterpret_cast<float*>(nsf_smem4);
+  float* s_win = smem;
+  float2* s_tw = reinterpret_cast<float2*>(smem + 256);
+  float* s_logi = smem + 768;
+
+  const int lane = lane_id();
+  const int warp = (int)(threadIdx.x >> 5);
+  const NsfTables* T = p.tables;
+  for (int i = (int)threadIdx.x; i < ANA; i += kNsfWarpsPerCta * 32)
+    s_win[i] = ANA == 256 ? T->win256[i] : T->win128[i];
+  for (int i = (int)threadIdx.x; i < 256; i += kNsfWarpsPerCta * 32) s_tw[i] = T->tw[i];
+  for (int i = (int)threadIdx.x; i < 132; i += kNsfWarpsPerCta * 32) s_logi[i] = T->logi[i];
+  __syncthreads();
+
+  const int sidx = (int)blockIdx.x * kNsfWarpsPerCta + warp;
+  if (sidx >= p.n_streams) return;  // whole warp leaves; no block barriers below
+
+  float* W = smem + kNsfCtaTableWords + warp * kNsfWarpWords;
+  // Header scalars are double buffered: within a frame every lane reads the
+  // frame-start copy (Hr) and writes the next copy (Hw) with warp-uniform
+  // values, so there is never a read-modify-write race between lanes.
+  float* Hr = W;
+  float* Hw = W + kNsfHdrWords;
+  float* B = W + 2 * kNsfHdrWords;            // per-bin records
+  float2* scr = reinterpret_cast<float2*>(B + 129 * kNsfBinRec);  // FFT scratch (8-byte aligned)
+
+  const int slot = p.slots[sidx];
+  float* gS = p.state + (size_t)slot * kNsfStateWords;
+  int* gHist = p.hist + (size_t)slot * kNsfHistWords;
+  float* gInitMagn = gS + kNsfOffInitMagn;
+
+  // ---- state: HBM -> shared / registers
+  Hr[lane] = gS[lane];
+  {
+    const float4* src = reinterpret_cast<const float4*>(gS + kNsfOffBins);
+    float4* dst = reinterpret_cast<float4*>(B);
+    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) dst[i] = src[i];
+  }
+  float2 hx[2], sy[2];       // analysis history / synthesis overlap, pair p = lane + 32u
+  float2 hb[NB > 1 ? NB - 1 : 1][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int pr = lane + 32 * u;
+    hx[u] = sy[u] = make_float2(0.f, 0.f);
+    if (pr < G::kHP) {
+      hx[u] = reinterpret_cast<const float2*>(gS + kNsfOffXHist)[pr];
+      sy[u] = reinterpret_cast<const float2*>(gS + kNsfOffSynt)[pr];
+    }
+#pragma unroll
+    for (int b = 0; b < NB - 1; ++b) {
+      hb[b][u] = make_float2(0.f, 0.f);
+      if (pr < G::kHP) hb[b][u] = reinterpret_cast<const float2*>(gS + kNsfOffHb + 96 * b)[pr];
+    }
+  }
+  __syncwarp();
+
+  const float overdrive = Hr[kH_overdrive];
+  const float denoiseBound = Hr[kH_denoiseBound];
+  const int gainmap = reinterpret_cast<const int*>(Hr)[kH_gainmap];
+  const float magnLenF = (float)G::kBins;
+
+  // PCM addressing: frame pair w of band b.
+  const size_t in_base = (size_t)sidx * (size_t)p.in_stream_stride;
+  const size_t out_base = (size_t)sidx * (size_t)p.out_stream_stride;
+  constexpr int kU = (G::kFP + 31) / 32;  // words per lane per band-frame (3 / 2)
+
+  // Raw frame words, prefetched one frame ahead.
+  float2 cur[NB][kU];
+  auto load_frame = [&](int f, float2 (&dst)[NB][kU]) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const size_t off = in_base + (size_t)f * (size_t)p.in_frame_stride + (size_t)b * (size_t)p.in_band_stride;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int w = lane + 32 * u;
+        dst[b][u] = make_float2(0.f, 0.f);
+        if (w < G::kFP) {
+          if (I16) {
+            const uint32_t v = reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.in) + off)[w];
+            dst[b][u] = make_float2((float)(int16_t)(v & 0xffffu), (float)(int16_t)(v >> 16));
+          } else {
+            dst[b][u] = reinterpret_cast<const float2*>(static_cast<const float*>(p.in) + off)[w];
+          }
+        }
+      }
+    }
+  };
+  auto store_pair = [&](int f, int b, int w, float2 v) {
+    const size_t off = out_base + (size_t)f * (size_t)p.out_frame_stride + (size_t)b * (size_t)p.out_band_stride;
+    if (I16) {
+      const uint32_t lo = (uint32_t)round_s16(v.x) & 0xffffu, hi = (uint32_t)round_s16(v.y) & 0xffffu;
+      reinterpret_cast<uint32_t*>(static_cast<int16_t*>(p.out) + off)[w] = lo | (hi << 16);
+    } else {
+      reinterpret_cast<float2*>(static_cast<float*>(p.out) + off)[w] = v;
+    }
+  };
+
+  if (p.frames > 0) load_frame(0, cur);
+
+  for (int f = 0; f < p.frames; ++f) {
+    float2 nxt[NB][kU] = {};
+    if (f + 1 < p.frames) load_frame(f + 1, nxt);
+
+    const int* HIr = reinterpret_cast<const int*>(Hr);
+    int* HIw = reinterpret_cast<int*>(Hw);
+    Hw[lane] = Hr[lane];  // ordered before any Hw update by the __syncwarp below
+
+    // ---- (a) UpdateBuffer: history | new frame -> scratch as sample pairs
+    // (all input was read into registers above, so out may alias in: ns_core.c:1225,1357)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hx[u];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[0][u];
+    __syncwarp();
+    float2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? scr[lane + G::kL * j] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (lane + 32 * u < G::kHP) hx[u] = scr[G::kFP + lane + 32 * u];
+    __syncwarp();
+
+    // ---- (b) Windowing + Energy (ns_core.c:1070-1071 / 1237-1238)
+    float energy1 = 0.f;
+    if (lane < G::kL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 w = reinterpret_cast<const float2*>(s_win)[lane + G::kL * j];
+        v[j].x *= w.x;
+        v[j].y *= w.y;
+        energy1 += v[j].x * v[j].x + v[j].y * v[j].y;
+      }
+    }
+    energy1 = warp_sum(energy1);
+
+    float2 o0[kU];  // band-0 output pairs
+    float hbGain = 1.f;
+    bool hbApplyGain = false;
+
+    if (energy1 == 0.f) {
+      // ---- zero input (ns_core.c:1072-1082, 1239-1264): no statistics update,
+      // flush the overlap, high bands pass through the delay line ungained.
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pr = lane + 32 * u;
+        o0[u] = (u < 2 && pr < G::kHP) ? sy[u < 2 ? u : 0] : make_float2(0.f, 0.f);
+      }
+      sy[0] = sy[1] = make_float2(0.f, 0.f);
+    } else {
+      const int blockInd = HIr[kH_blockInd] + 1;
+      HIw[kH_blockInd] = blockInd;
+      const int updateParsFlag = HIr[kH_modelUpd0];
+
+      // ---- (c) forward FFT (ns_core.c:886-911)
+      warp_fft<G::kNC, +1>(v, scr, s_tw, lane);
+      if (lane < G::kL) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
+      }
+      __syncwarp();
+
+      float re[G::kSlots], im[G::kSlots], magn[G::kSlots], lmagn[G::kSlots];
+      float sigE = 0.f, sumMagn = 0.f;
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const int k = nyq ? G::kNC : lane + 32 * j;
+        const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
+        const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
+        const float2 w = s_tw[k * (256 / ANA)];
+        const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+        const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
+        re[j] = er + (orr * w.x - oi * w.y);
+        im[j] = ei + (orr * w.y + oi * w.x);
+        if (nyq || k == 0) im[j] = 0.f;
+        magn[j] = sqrtf(re[j] * re[j] + im[j] * im[j]) + 1.f;
+        lmagn[j] = logf(magn[j]);
+        if (!nyq || lane == 0) {
+          sigE += re[j] * re[j] + im[j] * im[j];
+          sumMagn += magn[j];
+        }
+      }
+      __syncwarp();  // scratch is free again
+      warp_sum2(sigE, sumMagn);
+      const float signalEnergy = sigE / magnLenF;
+
+      // ---- (d) NoiseEstimation (ns_core.c:217-285)
+      int updates = HIr[kH_updates];
+      if (updates < 200) updates++;
+      HIw[kH_updates] = updates;
+      int cnt[3];
+      bool latch[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        cnt[s] = HIr[kH_counter + s];
+        latch[s] = cnt[s] >= 200;
+        HIw[kH_counter + s] = (latch[s] ? 0 : cnt[s]) + 1;
+      }
+      float noise[G::kSlots];
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const int k = nyq ? G::kNC : lane + 32 * j;
+        float* R = B + k * kNsfBinRec;
+        float4 r0 = *reinterpret_cast<float4*>(R);      // lq0 lq1 lq2 dens0
+        float4 r1 = *reinterpret_cast<float4*>(R + 4);  // dens1 dens2 quantile smooth
+        float lq[3] = {r0.x, r0.y, r0.z};
+        float dn[3] = {r0.w, r1.x, r1.y};
+        float quant = r1.z;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const float c1 = (float)(cnt[s] + 1);
+          const float delta = dn[s] > 1.f ? 40.f / dn[s] : 40.f;
+          if (lmagn[j] > lq[s]) lq[s] += 0.25f * delta / c1;
+          else lq[s] -= (1.f - 0.25f) * delta / c1;
+          if (fabsf(lmagn[j] - lq[s]) < 0.01f)
+            dn[s] = ((float)cnt[s] * dn[s] + 1.f / (2.f * 0.01f)) / c1;
+          if (latch[s] && updates >= 200) quant = expf(lq[s]);
+        }
+        if (updates < 200) quant = expf(lq[2]);
+        noise[j] = quant;
+        if (!nyq || lane == 0) {
+          *reinterpret_cast<float4*>(R) = make_float4(lq[0], lq[1], lq[2], dn[0]);
+          R[kB_dens1] = dn[1];
+          R[kB_dens2] = dn[2];
+          R[kB_quantile] = quant;
+        }
+      }
+
+      // ---- (e) start-up: white / pink parametric noise (ns_core.c:1088-1162)
+      float parametric[G::kSlots];
+      if (blockInd < 50) {
+        float slm = 0.f, slilm = 0.f;
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
+          if (k >= 5 && (!nyq || lane == 0)) {
+            slm += lmagn[j];
+            slilm += s_logi[k] * lmagn[j];
+          }
+        }
+        warp_sum2(slm, slilm);
+        const float sli = T->sum_log_i[ANA == 256 ? 0 : 1];
+        const float slisq = T->sum_log_i_sq[ANA == 256 ? 0 : 1];
+        float white = Hr[kH_white] + sumMagn / magnLenF * overdrive;
+        Hw[kH_white] = white;
+        float t1 = slisq * (float)(G::kBins - 5);
+        t1 -= sli * sli;
+        float t2 = slisq * slm - sli * slilm;
+        float t3 = t2 / t1;
+        if (t3 < 0.f) t3 = 0.f;
+        const float pinkNum = Hr[kH_pinkNum] + t3;
+        Hw[kH_pinkNum] = pinkNum;
+        t2 = sli * slm;
+        t2 -= (float)(G::kBins - 5) * slilm;
+        t3 = t2 / t1;
+        if (t3 < 0.f) t3 = 0.f;
+        if (t3 > 1.f) t3 = 1.f;
+        const float pinkExp = Hr[kH_pinkExp] + t3;
+        Hw[kH_pinkExp] = pinkExp;
+        float pnum = 0.f, pexp = 0.f;
+        if (pinkExp > 0.f) {
+          pnum = expf(pinkNum / (float)(blockInd + 1));
+          pnum *= (float)(blockInd + 1);
+          pexp = pinkExp / (float)(blockInd + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
+          if (pinkExp == 0.f) {
+            parametric[j] = white;
+          } else {
+            const float ub = (float)(k < 5 ? 5 : k);
+            parametric[j] = pnum / powf(ub, pexp);
+          }
+          noise[j] *= (float)blockInd;
+          const float t = parametric[j] * (float)(50 - blockInd);
+          noise[j] += t / (float)(blockInd + 1);
+          noise[j] /= 50.f;
+        }
+      }
+      // ---- (f) running energy normaliser (ns_core.c:1165-1169)
+      float feat5 = Hr[kH_feat + 5];
+      if (blockInd < 200) {
+        feat5 *= (float)blockInd;
+        feat5 += signalEnergy;
+        feat5 /= (float)(blockInd + 1);
+        Hw[kH_feat + 5] = feat5;
+      }
+
+      // ---- (g) ComputeSnr (ns_core.c:566-588) + feature sums
+      float prevEst[G::kSlots], snrPrior[G::kSlots], snrPost[G::kSlots];
+      float mpause[G::kSlots], noisePrev[G::kSlots], logLrt[G::kSlots];
+      float sumPause = 0.f, sumLog = 0.f;
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const int k = nyq ? G::kNC : lane + 32 * j;
+        const float* R = B + k * kNsfBinRec;
+        const float smooth = R[kB_smooth];
+        const float4 r2 = *reinterpret_cast<const float4*>(R + 8);  // noisePrev magnPrev logLrt pause
+        noisePrev[j] = r2.x;
+        logLrt[j] = r2.z;
+        mpause[j] = r2.w;
+        prevEst[j] = r2.y / (r2.x + 0.0001f) * smooth;
+        snrPost[j] = 0.f;
+        if (magn[j] > noise[j]) snrPost[j] = magn[j] / (noise[j] + 0.0001f) - 1.f;
+        snrPrior[j] = 0.98f * prevEst[j] + (1.f - 0.98f) * snrPost[j];
+        if (!nyq || lane == 0) {
+          sumPause += mpause[j];
+          if (k >= 1) sumLog += lmagn[j];
+        }
+      }
+      warp_sum2(sumPause, sumLog);
+
+      // ---- (h) FeatureUpdate (ns_core.c:755-791)
+      float feat0, feat4, prior;
+      {
+        // spectral flatness (:523-556); magn >= 1 so the log(0) exit is dead
+        float den = sumMagn - __shfl_sync(kFullMask, magn[0], 0);
+        den = den / magnLenF;
+        const float num = sumLog / magnLenF;
+        const float sf = expf(num) / den;
+        feat0 = Hr[kH_feat + 0];
+        feat0 += 0.3f * (sf - feat0);
+        Hw[kH_feat + 0] = feat0;
+        // spectral difference (:595-634)
+        const float avgPause = sumPause / magnLenF;
+        const float avgMagn = sumMagn / magnLenF;
+        float cov = 0.f, varP = 0.f, varM = 0.f;
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          if (!nyq || lane == 0) {
+            const float dm = magn[j] - avgMagn, dp = mpause[j] - avgPause;
+            cov += dm * dp;
+            varP += dp * dp;
+            varM += dm * dm;
+          }
+        }
+        warp_sum3(cov, varP, varM);
+        cov /= magnLenF;
+        varP /= magnLenF;
+        varM /= magnLenF;
+        float feat6 = Hr[kH_feat + 6] + signalEnergy;
+        float ad = varM - (cov * cov) / (varP + 0.0001f);
+        ad = ad / (feat5 + 0.0001f);
+        feat4 = Hr[kH_feat + 4];
+        feat4 += 0.3f * (ad - feat4);
+        Hw[kH_feat + 4] = feat4;
+        if (updateParsFlag >= 1) {
+          int c3 = HIr[kH_modelUpd3] - 1;
+          if (c3 > 0) {
+            // histogram update (:309-334) -- uses the LRT mean of the previous frame
+            if (lane == 0) {
+              const float f3 = Hr[kH_feat + 3];
+              if (f3 < 1000 * 0.1f && f3 >= 0.f) atomicAdd(gHist + (int)(f3 / 0.1f), 1);
+              if (feat0 < 1000 * 0.05f && feat0 >= 0.f) atomicAdd(gHist + 1000 + (int)(feat0 / 0.05f), 1);
+              if (feat4 < 1000 * 0.1f && feat4 >= 0.f) atomicAdd(gHist + 2000 + (int)(feat4 / 0.1f), 1);
+            }
+          }
+          if (c3 == 0) {
+            __threadfence_block();
+            __syncwarp();
+            nsf_extract_params(Hw, gHist, lane);
+            c3 = 500;
+            if (updateParsFlag == 1) {
+              HIw[kH_modelUpd0] = 0;
+            } else {
+              feat6 = feat6 / 500.f;
+              feat5 = 0.5f * (feat6 + feat5);
+              Hw[kH_feat + 5] = feat5;
+              feat6 = 0.f;
+            }
+          }
+          HIw[kH_modelUpd3] = c3;
+        }
+        Hw[kH_feat + 6] = feat6;
+        __syncwarp();
+      }
+
+      // ---- (i) SpeechNoiseProb (ns_core.c:642-749)
+      float prob[G::kSlots];
+      {
+        float lsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const float t1 = 1.f + 2.f * snrPrior[j];
+          const float t2 = 2.f * snrPrior[j] / (t1 + 0.0001f);
+          const float bessel = (snrPost[j] + 1.f) * t2;
+          logLrt[j] += 0.5f * (bessel - logf(t1) - logLrt[j]);
+          if (!nyq || lane == 0) lsum += logLrt[j];
+        }
+        lsum = warp_sum(lsum);
+        const float lrtAvg = lsum / magnLenF;
+        Hw[kH_feat + 3] = lrtAvg;
+        // priorModelPars may have been re-estimated a few lines up (synced): read Hw
+        const float thr0 = Hw[kH_priorPars + 0], thr1 = Hw[kH_priorPars + 1], thr2 = Hw[kH_priorPars + 3];
+        const int sgn = (int)Hw[kH_priorPars + 2];
+        float width = lrtAvg < thr0 ? 8.f : 4.f;
+        const float ind0 = 0.5f * (tanhf(width * (lrtAvg - thr0)) + 1.f);
+        const float sfv = feat0;
+        width = 4.f;
+        if (sgn == 1 && sfv > thr1) width = 8.f;
+        if (sgn == -1 && sfv < thr1) width = 8.f;
+        const float ind1 = 0.5f * (tanhf((float)sgn * width * (thr1 - sfv)) + 1.f);
+        const float sdv = feat4;
+        width = sdv < thr2 ? 8.f : 4.f;
+        const float ind2 = 0.5f * (tanhf(width * (sdv - thr2)) + 1.f);
+        const float indPrior = Hw[kH_priorPars + 4] * ind0 + Hw[kH_priorPars + 5] * ind1 +
+                               Hw[kH_priorPars + 6] * ind2;
+        prior = Hr[kH_priorSpeechProb];
+        prior += 0.1f * (indPrior - prior);
+        if (prior > 1.f) prior = 1.f;
+        if (prior < 0.01f) prior = 0.01f;
+        Hw[kH_priorSpeechProb] = prior;
+        const float gainPrior = (1.f - prior) / (prior + 0.0001f);
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          float inv = expf(-logLrt[j]);
+          inv = gainPrior * inv;
+          prob[j] = 1.f / (1.f + inv);
+        }
+      }
+
+      // ---- (j) UpdateNoiseEstimate (ns_core.c:800-846): gamma carried from bin i-1
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        float pprev;  // speech probability of bin k-1
+        if (nyq) {
+          pprev = __shfl_sync(kFullMask, prob[G::kSlots - 2], 31);
+        } else {
+          pprev = __shfl_up_sync(kFullMask, prob[j], 1);
+          const float wrap = __shfl_sync(kFullMask, prob[j > 0 ? j - 1 : 0], 31);
+          if (lane == 0) pprev = wrap;
+        }
+        const bool first = (!nyq && j == 0 && lane == 0);
+        const float gOld = (!first && pprev > 0.2f) ? 0.99f : 0.9f;
+        const float ps = prob[j], pn = 1.f - ps;
+        const float mix = pn * magn[j] + ps * noisePrev[j];
+        const float nTmp = gOld * noisePrev[j] + (1.f - gOld) * mix;
+        const float gNew = ps > 0.2f ? 0.99f : 0.9f;
+        if (ps < 0.2f) mpause[j] += 0.05f * (magn[j] - mpause[j]);
+        float nz;
+        if (gNew == gOld) {
+          nz = nTmp;
+        } else {
+          nz = gNew * noisePrev[j] + (1.f - gNew) * mix;
+          if (nTmp < nz) nz = nTmp;
+        }
+        noise[j] = nz;
+      }
+
+      // ---- (k) Wiener filter, flooring, start-up blend (ns_core.c:985-1007, 1268-1307)
+      float hbProbSum = 0.f, hbGainSum = 0.f;
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const int k = nyq ? G::kNC : lane + 32 * j;
+        float cur_est = 0.f;
+        if (magn[j] > noise[j]) cur_est = magn[j] / (noise[j] + 0.0001f) - 1.f;
+        const float sp = 0.98f * prevEst[j] + (1.f - 0.98f) * cur_est;
+        float flt = sp / (overdrive + sp);
+        if (flt < denoiseBound) flt = denoiseBound;
+        if (flt > 1.f) flt = 1.f;
+        if (blockInd < 50) {
+          float ime = gInitMagn[k] + magn[j];
+          if (!nyq || lane == 0) gInitMagn[k] = ime;
+          float ft = ime - overdrive * parametric[j];
+          ft /= (ime + 0.0001f);
+          if (ft < denoiseBound) ft = denoiseBound;
+          if (ft > 1.f) ft = 1.f;
+          flt *= (float)blockInd;
+          ft *= (float)(50 - blockInd);
+          flt += ft;
+          flt /= 50.f;
+        }
+        re[j] *= flt;
+        im[j] *= flt;
+        if (!nyq || lane == 0) {
+          float* R = B + k * kNsfBinRec;
+          R[kB_smooth] = flt;
+          *reinterpret_cast<float4*>(R + 8) = make_float4(noise[j], magn[j], logLrt[j], mpause[j]);
+          scr[k] = make_float2(re[j], im[j]);
+        }
+        if (NB > 1) {
+          // averages over the top quarter of the band, bins [magnLen - d - 1, magnLen - 1)
+          constexpr int d = G::kBins / 4;
+          if (!nyq && k >= G::kBins - d - 1 && k < G::kBins - 1) {
+            hbProbSum += prob[j];
+            hbGainSum += flt;
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- (l) inverse FFT (ns_core.c:923-944)
+      if (lane < G::kL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = lane + G::kL * j;
+          const float2 xk = scr[k];
+          const float2 xm = scr[G::kNC - k];
+          const float2 w = s_tw[k * (256 / ANA)];
+          const float er = 0.5f * (xk.x + xm.x), ei = 0.5f * (xk.y - xm.y);
+          const float dr = 0.5f * (xk.x - xm.x), di = 0.5f * (xk.y + xm.y);
+          // O = (dr + i di) * conj(w);  Z = E + i O
+          const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+          v[j] = make_float2(er - oi, ei + orr);
+        }
+      }
+      __syncwarp();
+      warp_fft<G::kNC, -1>(v, scr, s_tw, lane);
+      if (lane < G::kL) {
+        const float sc = 2.f / (float)ANA;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = make_float2(v[q].x * sc, v[q].y * sc);
+      }
+      __syncwarp();
+
+      // ---- (m) gain compensation, window, overlap-add (ns_core.c:1314-1359)
+      constexpr int kTU = G::kTP / 32;  // pairs per lane over the whole block (4 / 2)
+      float2 y[kTU];
+      float energy2 = 0.f;
+#pragma unroll
+      for (int u = 0; u < kTU; ++u) {
+        y[u] = scr[pad_idx(lane + 32 * u)];
+        energy2 += y[u].x * y[u].x + y[u].y * y[u].y;
+      }
+      float factor = 1.f;
+      if (gainmap == 1 && blockInd > 200) {
+        energy2 = warp_sum(energy2);
+        float factor1 = 1.f, factor2 = 1.f;
+        float gain = sqrtf(energy2 / (energy1 + 1.f));
+        if (gain > 0.5f) {
+          factor1 = 1.f + 1.3f * (gain - 0.5f);
+          if (gain * factor1 > 1.f) factor1 = 1.f / gain;
+        }
+        if (gain < 0.5f) {
+          if (gain <= denoiseBound) gain = denoiseBound;
+          factor2 = 1.f - 0.3f * (0.5f - gain);
+        }
+        factor = prior * factor1 + (1.f - prior) * factor2;
+      }
+      // windowed, scaled pairs back to scratch so that the tail can be re-read
+      // in overlap order
+#pragma unroll
+      for (int u = 0; u < kTU; ++u) {
+        const float2 w = reinterpret_cast<const float2*>(s_win)[lane + 32 * u];
+        y[u] = make_float2(factor * (w.x * y[u].x), factor * (w.y * y[u].y));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < kTU; ++u) scr[lane + 32 * u] = y[u];
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pr = lane + 32 * u;
+        float2 o = make_float2(0.f, 0.f);
+        if (pr < G::kFP) {
+          o = scr[pr];
+          if (u < 2 && pr < G::kHP) { o.x += sy[u < 2 ? u : 0].x; o.y += sy[u < 2 ? u : 0].y; }
+        }
+        o0[u] = make_float2(sat_s16f(o.x), sat_s16f(o.y));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < G::kHP) sy[u] = scr[G::kFP + lane + 32 * u];
+      __syncwarp();
+
+      // ---- (n) high-band time-domain gain (ns_core.c:1362-1404)
+      if (NB > 1) {
+        constexpr int d = G::kBins / 4;
+        warp_sum2(hbProbSum, hbGainSum);
+        float avgProb = hbProbSum / (float)d;
+        // sumMagnProcess / sumMagnAnalyze == 1 when Analyze and Process see one frame
+        const float avgGain = hbGainSum / (float)d;
+        const float tmp = 2.f * avgProb - 1.f;
+        const float gmod = 0.5f * (1.f + tanhf(tmp));
+        float g = 0.5f * gmod + 0.5f * avgGain;
+        if (avgProb >= 0.5f) g = 0.25f * gmod + 0.75f * avgGain;
+        if (g < denoiseBound) g = denoiseBound;
+        if (g > 1.f) g = 1.f;
+        hbGain = g;
+        hbApplyGain = true;
+      }
+    }
+
+    // ---- outputs
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lane + 32 * u < G::kFP) store_pair(f, 0, lane + 32 * u, o0[u]);
+
+    if (NB > 1) {
+      // delay line of 2*kHP samples per high band (dataBufHB, ns_core.c:1227-1235);
+      // output = oldest kFrame samples of [history | new frame]
+#pragma unroll
+      for (int b = 0; b < NB - 1; ++b) {
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hb[b][u];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[b + 1 < NB ? b + 1 : 0][u];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int pr = lane + 32 * u;
+          if (pr < G::kFP) {
+            float2 o = scr[pr];
+            if (hbApplyGain) { o.x *= hbGain; o.y *= hbGain; }
+            store_pair(f, b + 1, pr, make_float2(sat_s16f(o.x), sat_s16f(o.y)));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) hb[b][u] = scr[G::kFP + lane + 32 * u];
+      }
+      __syncwarp();
+    }
+
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int u = 0; u < kU; ++u) cur[b][u] = nxt[b][u];
+    __syncwarp();
+    { float* t = Hr; Hr = Hw; Hw = t; }
+  }
+
+  // ---- state: shared / registers -> HBM
+  __syncwarp();
+  gS[lane] = Hr[lane];
+  {
+    float4* dst = reinterpret_cast<float4*>(gS + kNsfOffBins);
+    const float4* src = reinterpret_cast<const float4*>(B);
+    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) dst[i] = src[i];
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int pr = lane + 32 * u;
+    if (pr < G::kHP) {
+      reinterpret_cast<float2*>(gS + kNsfOffXHist)[pr] = hx[u];
+      reinterpret_cast<float2*>(gS + kNsfOffSynt)[pr] = sy[u];
+#pragma unroll
+      for (int b = 0; b < NB - 1; ++b) reinterpret_cast<float2*>(gS + kNsfOffHb + 96 * b)[pr] = hb[b][u];
+    }
+  }
+}
+
+}  // namespace nsb200
+
+#endif  // AUDIOSIGNALPROCESS_B200_NSF_KERNEL_CUH_
