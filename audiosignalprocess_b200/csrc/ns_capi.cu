@@ -1,0 +1,902 @@
+// C-ABI host layer of libwebrtc_ns_b200.so (include/webrtc_ns_b200.h).
+//
+// Mirrors the reference's thin C wrappers (ns/noise_suppression.c:20-66,
+// ns/noise_suppression_x.c:19-54): a handle is a small host struct that names a
+// slot in a per-GPU state slab; Create/Init/set_policy edit that slot, the
+// batch calls hand a list of slots to one kernel launch.  No CPU compute path
+// exists here: without a usable GPU every call fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/webrtc_ns_b200.h"
+#include "nsf_host_init.h"
+#include "nsf_kernel.cuh"
+#include "nsx_host_init.h"
+#include "nsx_kernel.cuh"
+#include "band_kernels.cuh"
+#include "pcm_synth.h"
+
+namespace nsb200 {
+namespace {
+
+std::mutex g_mu;
+std::string g_err;
+uint64_t g_launches = 0;
+int g_create_device = -1;
+
+int Fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+#define CU_OK(call)                                                              \
+  do {                                                                           \
+    cudaError_t e_ = (call);                                                     \
+    if (e_ != cudaSuccess)                                                       \
+      return Fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+constexpr uint32_t kMagicF = 0x4e53464cu;  // float handle
+constexpr uint32_t kMagicX = 0x4e535846u;  // fixed handle
+
+struct Handle {
+  uint32_t magic;
+  int dev;
+  int slot;
+  uint32_t fs;
+  int mode;
+  int init_flag;
+  bool analyze_seen;
+  float analyze_frame[160];
+};
+
+// Growable pool of fixed-size slabs in device memory.
+struct SlabPool {
+  void* base = nullptr;
+  size_t slab_bytes = 0;
+  int capacity = 0;
+  std::vector<int> free_slots;
+  int next = 0;
+};
+
+struct DeviceCtx {
+  int dev = -1;
+  bool ready = false;
+  cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+  NsfTables* d_nsf_tables = nullptr;
+  NsxTables* d_nsx_tables = nullptr;
+  SlabPool f_state, f_hist, x_state, b_state;  // float state, float histograms, fixed state, band-split state
+  void* d_template = nullptr;   // scratch for Init templates
+  size_t template_bytes = 0;
+  int* d_slots = nullptr;       // slot list of the current batch
+  int* h_slots = nullptr;       // pinned
+  int slots_cap = 0;
+  std::vector<int> cached_slots;
+  // device staging for the host-pointer batch API
+  int16_t* d_in = nullptr;
+  int16_t* d_out = nullptr;
+  size_t stage_elems = 0;
+  int16_t* d_bands = nullptr;   // [stream][frame][band][160] scratch for 32/48 kHz
+  size_t bands_elems = 0;
+};
+
+std::vector<DeviceCtx> g_devs;
+
+int EnsureDevices() {
+  if (!g_devs.empty()) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return Fail(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
+  g_devs.resize(n);
+  for (int i = 0; i < n; ++i) g_devs[i].dev = i;
+  return 0;
+}
+
+int PoolGrow(DeviceCtx& d, SlabPool& p, int want) {
+  if (want <= p.capacity) return 0;
+  int cap = p.capacity ? p.capacity : 1024;
+  while (cap < want) cap *= 2;
+  void* nb = nullptr;
+  CU_OK(cudaMalloc(&nb, (size_t)cap * p.slab_bytes));
+  if (p.base) {
+    CU_OK(cudaDeviceSynchronize());
+    CU_OK(cudaMemcpy(nb, p.base, (size_t)p.capacity * p.slab_bytes, cudaMemcpyDeviceToDevice));
+    CU_OK(cudaFree(p.base));
+  }
+  p.base = nb;
+  p.capacity = cap;
+  return 0;
+}
+
+int PoolAlloc(DeviceCtx& d, SlabPool& p, int* slot) {
+  if (!p.free_slots.empty()) {
+    *slot = p.free_slots.back();
+    p.free_slots.pop_back();
+    return 0;
+  }
+  if (p.next >= p.capacity && PoolGrow(d, p, p.next + 1) != 0) return -1;
+  *slot = p.next++;
+  return 0;
+}
+
+int DeviceReady(int dev, DeviceCtx** out) {
+  if (EnsureDevices() != 0) return -1;
+  if (dev < 0 || dev >= (int)g_devs.size()) return Fail("bad device index");
+  DeviceCtx& d = g_devs[dev];
+  CU_OK(cudaSetDevice(dev));
+  if (!d.ready) {
+    CU_OK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CU_OK(cudaStreamCreateWithFlags(&d.copy_in, cudaStreamNonBlocking));
+    CU_OK(cudaStreamCreateWithFlags(&d.copy_out, cudaStreamNonBlocking));
+    {
+      NsfTables* t = new NsfTables;
+      nsf_fill_tables(t);
+      CU_OK(cudaMalloc(&d.d_nsf_tables, sizeof(NsfTables)));
+      CU_OK(cudaMemcpy(d.d_nsf_tables, t, sizeof(NsfTables), cudaMemcpyHostToDevice));
+      delete t;
+    }
+    {
+      NsxTables* t = new NsxTables;
+      nsx_fill_tables(t);
+      CU_OK(cudaMalloc(&d.d_nsx_tables, sizeof(NsxTables)));
+      CU_OK(cudaMemcpy(d.d_nsx_tables, t, sizeof(NsxTables), cudaMemcpyHostToDevice));
+      delete t;
+    }
+    d.f_state.slab_bytes = sizeof(uint32_t) * kNsfStateWords;
+    d.f_hist.slab_bytes = sizeof(uint32_t) * kNsfHistWords;
+    d.x_state.slab_bytes = sizeof(uint32_t) * kNsxStateWords;
+    d.b_state.slab_bytes = sizeof(uint32_t) * kBandStateWords;
+    {
+      int w = kNsfStateWords > kNsxStateWords ? kNsfStateWords : kNsxStateWords;
+      if (kBandStateWords > w) w = kBandStateWords;
+      d.template_bytes = sizeof(uint32_t) * w;
+    }
+    CU_OK(cudaMalloc(&d.d_template, d.template_bytes));
+    d.ready = true;
+  }
+  *out = &d;
+  return 0;
+}
+
+Handle* AsHandle(void* h, uint32_t magic) {
+  Handle* p = static_cast<Handle*>(h);
+  return (p && p->magic == magic) ? p : nullptr;
+}
+
+// ---- init: copy a template slab into each listed slot, zero the cold slab ----
+__global__ void slab_fill_kernel(uint32_t* base, int words, const uint32_t* tmpl, const int* slots,
+                                 int n, uint32_t* cold, int cold_words, uint32_t* aux, int aux_words) {
+  const int s = blockIdx.x;
+  if (s >= n) return;
+  const int slot = slots[s];
+  uint32_t* dst = base + (size_t)slot * words;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = tmpl[i];
+  if (cold) {
+    uint32_t* c = cold + (size_t)slot * cold_words;
+    for (int i = threadIdx.x; i < cold_words; i += blockDim.x) c[i] = 0u;
+  }
+  if (aux) {
+    uint32_t* a = aux + (size_t)slot * aux_words;
+    for (int i = threadIdx.x; i < aux_words; i += blockDim.x) a[i] = 0u;
+  }
+}
+
+int UploadSlots(DeviceCtx& d, const std::vector<int>& slots, cudaStream_t st) {
+  const int n = (int)slots.size();
+  if (n > d.slots_cap) {
+    if (d.d_slots) {
+      CU_OK(cudaDeviceSynchronize());
+      CU_OK(cudaFree(d.d_slots));
+      CU_OK(cudaFreeHost(d.h_slots));
+    }
+    int cap = 1024;
+    while (cap < n) cap *= 2;
+    CU_OK(cudaMalloc(&d.d_slots, sizeof(int) * cap));
+    CU_OK(cudaMallocHost(&d.h_slots, sizeof(int) * cap));
+    d.slots_cap = cap;
+    d.cached_slots.clear();
+  }
+  if (d.cached_slots == slots) return 0;  // same batch as last call: list already resident
+  // a kernel of the previous batch (on any stream) may still be reading the old list
+  CU_OK(cudaDeviceSynchronize());
+  memcpy(d.h_slots, slots.data(), sizeof(int) * n);
+  CU_OK(cudaMemcpyAsync(d.d_slots, d.h_slots, sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
+  if (st != d.stream) CU_OK(cudaStreamSynchronize(d.stream));
+  d.cached_slots = slots;
+  return 0;
+}
+
+int Create(void** out, uint32_t magic) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return Fail("NULL handle pointer");
+  *out = nullptr;
+  int dev = g_create_device;
+  if (dev < 0) {
+    if (EnsureDevices() != 0) return -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return Fail("cudaGetDevice failed");
+  }
+  DeviceCtx* d;
+  if (DeviceReady(dev, &d) != 0) return -1;
+  Handle* h = new Handle();
+  h->magic = magic;
+  h->dev = dev;
+  h->init_flag = 0;
+  h->fs = 0;
+  h->mode = 0;
+  h->analyze_seen = false;
+  int rc;
+  if (magic == kMagicF) {
+    rc = PoolAlloc(*d, d->f_state, &h->slot);
+    if (rc == 0 && PoolGrow(*d, d->f_hist, d->f_state.capacity) != 0) rc = -1;
+  } else {
+    rc = PoolAlloc(*d, d->x_state, &h->slot);
+  }
+  if (rc == 0 && PoolGrow(*d, d->b_state, 2 * (magic == kMagicF ? d->f_state : d->x_state).capacity) != 0) rc = -1;
+  if (rc != 0) {
+    delete h;
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+int Free(void* hv, uint32_t magic) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AsHandle(hv, magic);
+  if (!h) return 0;  // reference: free(NULL) is fine, returns 0
+  DeviceCtx& d = g_devs[h->dev];
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(d.stream);
+  (magic == kMagicF ? d.f_state : d.x_state).free_slots.push_back(h->slot);
+  d.cached_slots.clear();
+  h->magic = 0;
+  delete h;
+  return 0;
+}
+
+// Band-split state shares the slot index of the owning (float or fixed) handle;
+// float and fixed handles use disjoint halves of the band pool.
+int BandSlot(const Handle* h) { return h->magic == kMagicF ? 2 * h->slot : 2 * h->slot + 1; }
+
+int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!hv || n <= 0) return Fail("no handles");
+  if (!(fs == 8000 || fs == 16000 || fs == 32000 || fs == 48000)) return Fail("unsupported fs");
+  if (mode < 0 || mode > 3) return Fail("mode out of range");
+  std::vector<std::vector<int>> per_dev(g_devs.size());
+  for (int i = 0; i < n; ++i) {
+    Handle* h = AsHandle(hv[i], magic);
+    if (!h) return Fail("bad handle");
+    per_dev[h->dev].push_back(i);
+  }
+  for (size_t dv = 0; dv < per_dev.size(); ++dv) {
+    if (per_dev[dv].empty()) continue;
+    DeviceCtx* d;
+    if (DeviceReady((int)dv, &d) != 0) return -1;
+    std::vector<int> slots, bslots;
+    for (int i : per_dev[dv]) {
+      Handle* h = static_cast<Handle*>(hv[i]);
+      slots.push_back(h->slot);
+      bslots.push_back(BandSlot(h));
+    }
+    std::vector<uint32_t> tmpl(d->template_bytes / 4, 0u);
+    int words;
+    if (magic == kMagicF) {
+      nsf_init_state(tmpl.data(), fs);
+      nsf_set_mode(tmpl.data(), mode);
+      words = kNsfStateWords;
+    } else {
+      nsx_init_state(tmpl.data(), fs);
+      nsx_set_mode(tmpl.data(), mode);
+      words = kNsxStateWords;
+    }
+    CU_OK(cudaStreamSynchronize(d->stream));
+    CU_OK(cudaMemcpyAsync(d->d_template, tmpl.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice, d->stream));
+    if (PoolGrow(*d, d->b_state, 2 * (magic == kMagicF ? d->f_state : d->x_state).capacity) != 0) return -1;
+    if (UploadSlots(*d, slots, d->stream) != 0) return -1;
+    const int m = (int)slots.size();
+    if (magic == kMagicF) {
+      slab_fill_kernel<<<m, 256, 0, d->stream>>>((uint32_t*)d->f_state.base, kNsfStateWords,
+                                                 (const uint32_t*)d->d_template, d->d_slots, m,
+                                                 (uint32_t*)d->f_hist.base, kNsfHistWords, nullptr, 0);
+    } else {
+      slab_fill_kernel<<<m, 256, 0, d->stream>>>((uint32_t*)d->x_state.base, kNsxStateWords,
+                                                 (const uint32_t*)d->d_template, d->d_slots, m,
+                                                 nullptr, 0, nullptr, 0);
+    }
+    ++g_launches;
+    // band-split state: zero (TwoBandsStates ctor, splitting_filter.h:34-39; resampler priming)
+    if (UploadSlots(*d, bslots, d->stream) != 0) return -1;
+    CU_OK(cudaMemsetAsync(d->d_template, 0, d->template_bytes, d->stream));
+    slab_fill_kernel<<<m, 256, 0, d->stream>>>((uint32_t*)d->b_state.base, kBandStateWords,
+                                               (const uint32_t*)d->d_template, d->d_slots, m,
+                                               nullptr, 0, nullptr, 0);
+    ++g_launches;
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(d->stream));
+    d->cached_slots.clear();
+  }
+  for (int i = 0; i < n; ++i) {
+    Handle* h = static_cast<Handle*>(hv[i]);
+    h->fs = fs;
+    h->mode = mode;
+    h->init_flag = 1;
+    h->analyze_seen = false;
+  }
+  return 0;
+}
+
+int SetPolicy(void* hv, int mode, uint32_t magic) {
+  Handle* h;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    h = AsHandle(hv, magic);
+    if (!h) return Fail("bad handle");
+    if (mode < 0 || mode > 3) return Fail("mode out of range");
+    if (!h->init_flag) {
+      // the reference only writes fields of the struct here; Init later resets
+      // them to mode 0, so this is a no-op before Init.
+      return 0;
+    }
+    DeviceCtx* d;
+    if (DeviceReady(h->dev, &d) != 0) return -1;
+    CU_OK(cudaStreamSynchronize(d->stream));
+    if (magic == kMagicF) {
+      uint32_t w[kNsfHdrWords];
+      uint32_t* slab = (uint32_t*)d->f_state.base + (size_t)h->slot * kNsfStateWords;
+      CU_OK(cudaMemcpy(w, slab, sizeof(w), cudaMemcpyDeviceToHost));
+      // nsf_set_mode touches header words only
+      std::vector<uint32_t> tmp(kNsfStateWords, 0u);
+      memcpy(tmp.data(), w, sizeof(w));
+      nsf_set_mode(tmp.data(), mode);
+      CU_OK(cudaMemcpy(slab, tmp.data(), sizeof(w), cudaMemcpyHostToDevice));
+    } else {
+      uint32_t w[kNsxHdrWords];
+      uint32_t* slab = (uint32_t*)d->x_state.base + (size_t)h->slot * kNsxStateWords;
+      CU_OK(cudaMemcpy(w, slab, sizeof(w), cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> tmp(kNsxStateWords, 0u);
+      memcpy(tmp.data(), w, sizeof(w));
+      nsx_set_mode(tmp.data(), mode);
+      CU_OK(cudaMemcpy(slab, tmp.data(), sizeof(w), cudaMemcpyHostToDevice));
+    }
+    h->mode = mode;
+  }
+  return 0;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------
+template <int ANA, int NB, bool I16>
+int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
+  const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
+  const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
+  nsf_process_kernel<ANA, NB, I16><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
+  ++g_launches;
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+int LaunchNsf(int ana, int nb, bool i16, const NsfLaunch& p, cudaStream_t st) {
+  if (ana == 128 && nb == 1) return i16 ? LaunchNsfT<128, 1, true>(p, st) : LaunchNsfT<128, 1, false>(p, st);
+  if (ana == 256 && nb == 1) return i16 ? LaunchNsfT<256, 1, true>(p, st) : LaunchNsfT<256, 1, false>(p, st);
+  if (ana == 256 && nb == 2) return i16 ? LaunchNsfT<256, 2, true>(p, st) : LaunchNsfT<256, 2, false>(p, st);
+  if (ana == 256 && nb == 3) return i16 ? LaunchNsfT<256, 3, true>(p, st) : LaunchNsfT<256, 3, false>(p, st);
+  return Fail("unsupported (fs, num_bands) combination");
+}
+
+template <int ANA, int NB>
+int LaunchNsxT(const NsxLaunch& p, cudaStream_t st) {
+  const int grid = (p.n_streams + kNsxWarpsPerCta - 1) / kNsxWarpsPerCta;
+  const size_t smem = sizeof(uint32_t) * (kNsxCtaTableWords + kNsxWarpsPerCta * kNsxWarpWords);
+  nsx_process_kernel<ANA, NB><<<grid, kNsxWarpsPerCta * 32, smem, st>>>(p);
+  ++g_launches;
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+int LaunchNsx(int ana, int nb, const NsxLaunch& p, cudaStream_t st) {
+  if (ana == 128 && nb == 1) return LaunchNsxT<128, 1>(p, st);
+  if (ana == 256 && nb == 1) return LaunchNsxT<256, 1>(p, st);
+  if (ana == 256 && nb == 2) return LaunchNsxT<256, 2>(p, st);
+  if (ana == 256 && nb == 3) return LaunchNsxT<256, 3>(p, st);
+  return Fail("unsupported (fs, num_bands) combination");
+}
+
+int NumBands(uint32_t fs) { return fs == 32000 ? 2 : (fs == 48000 ? 3 : 1); }
+
+// Enqueues split -> NS -> merge for `idx.size()` streams of one device whose
+// full-band int16 PCM sits in device memory.
+int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, const int16_t* d_in,
+              size_t in_stride, int16_t* d_out, size_t out_stride, int frames, cudaStream_t st) {
+  const int n = (int)hs.size();
+  const uint32_t fs = hs[0]->fs;
+  const int nb = NumBands(fs);
+  const int fl = (int)fs / 100;
+  const int ana = fs == 8000 ? 128 : 256;
+  std::vector<int> slots(n), bslots(n);
+  for (int i = 0; i < n; ++i) {
+    slots[i] = hs[i]->slot;
+    bslots[i] = BandSlot(hs[i]);
+  }
+  const int16_t* ns_in = d_in;
+  int16_t* ns_out = d_out;
+  long long ns_in_ss = (long long)in_stride, ns_out_ss = (long long)out_stride;
+  long long fstride = fl, bstride = 0;
+  int* d_bslots = nullptr;
+  if (nb > 1) {
+    // band scratch [stream][frame][band][160], split in place of the NS input
+    const size_t need = (size_t)n * frames * nb * 160;
+    if (need > d.bands_elems) {
+      CU_OK(cudaStreamSynchronize(st));
+      if (d.d_bands) CU_OK(cudaFree(d.d_bands));
+      CU_OK(cudaMalloc(&d.d_bands, sizeof(int16_t) * need));
+      d.bands_elems = need;
+    }
+    ns_in = ns_out = d.d_bands;
+    ns_in_ss = ns_out_ss = (long long)frames * nb * 160;
+    fstride = nb * 160;
+    bstride = 160;
+  }
+  // slot lists: [0,n) = NS slots, [n,2n) = band slots
+  std::vector<int> all(slots);
+  if (nb > 1) all.insert(all.end(), bslots.begin(), bslots.end());
+  if (UploadSlots(d, all, st) != 0) return -1;
+  d_bslots = d.d_slots + n;
+
+  if (nb > 1) {
+    BandLaunch b;
+    b.state = (int32_t*)d.b_state.base;
+    b.slots = d_bslots;
+    b.full = const_cast<int16_t*>(d_in);
+    b.full_stride = (long long)in_stride;
+    b.bands = d.d_bands;
+    b.bands_stride = ns_in_ss;
+    b.n_streams = n;
+    b.frames = frames;
+    if (LaunchBandSplit(nb, b, st, &g_launches) != 0) return Fail("band split launch failed");
+  }
+  if (magic == kMagicF) {
+    NsfLaunch p;
+    p.state = (float*)d.f_state.base;
+    p.hist = (int*)d.f_hist.base;
+    p.slots = d.d_slots;
+    p.tables = d.d_nsf_tables;
+    p.in = ns_in;
+    p.out = ns_out;
+    p.in_stream_stride = ns_in_ss;
+    p.out_stream_stride = ns_out_ss;
+    p.in_frame_stride = p.out_frame_stride = fstride;
+    p.in_band_stride = p.out_band_stride = bstride;
+    p.n_streams = n;
+    p.frames = frames;
+    if (LaunchNsf(ana, nb, true, p, st) != 0) return -1;
+  } else {
+    NsxLaunch p;
+    p.state = (uint32_t*)d.x_state.base;
+    p.slots = d.d_slots;
+    p.tables = d.d_nsx_tables;
+    p.in = ns_in;
+    p.out = ns_out;
+    p.in_stream_stride = ns_in_ss;
+    p.out_stream_stride = ns_out_ss;
+    p.in_frame_stride = p.out_frame_stride = fstride;
+    p.in_band_stride = p.out_band_stride = bstride;
+    p.n_streams = n;
+    p.frames = frames;
+    if (LaunchNsx(ana, nb, p, st) != 0) return -1;
+  }
+  if (nb > 1) {
+    BandLaunch b;
+    b.state = (int32_t*)d.b_state.base;
+    b.slots = d_bslots;
+    b.full = d_out;
+    b.full_stride = (long long)out_stride;
+    b.bands = d.d_bands;
+    b.bands_stride = ns_in_ss;
+    b.n_streams = n;
+    b.frames = frames;
+    if (LaunchBandMerge(nb, b, st, &g_launches) != 0) return Fail("band merge launch failed");
+  }
+  return 0;
+}
+
+int CheckBatch(void* const* hv, int n, uint32_t magic, size_t in_stride, size_t out_stride,
+               int frames, std::vector<Handle*>* hs) {
+  if (!hv || n <= 0) return Fail("no handles");
+  if (frames < 0) return Fail("negative frame count");
+  if ((in_stride | out_stride) & 1) return Fail("strides must be even");
+  hs->resize(n);
+  for (int i = 0; i < n; ++i) {
+    Handle* h = AsHandle(hv[i], magic);
+    if (!h) return Fail("bad handle in batch");
+    if (!h->init_flag) return Fail("handle not initialised");
+    if (h->fs != static_cast<Handle*>(hv[0])->fs) return Fail("mixed sample rates in one batch");
+    (*hs)[i] = h;
+  }
+  const size_t need = (size_t)frames * ((*hs)[0]->fs / 100);
+  if (n > 1 && (in_stride < need || out_stride < need)) return Fail("stride shorter than the frames of one stream");
+  return 0;
+}
+
+int BatchDevice(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
+                int16_t* out, size_t out_stride, int frames, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<Handle*> hs;
+  if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (frames == 0) return 0;
+  for (int i = 1; i < n; ++i)
+    if (hs[i]->dev != hs[0]->dev) return Fail("device batch spans several GPUs");
+  DeviceCtx* d;
+  if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
+  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  return RunDevice(*d, magic, hs, in, in_stride, out, out_stride, frames, st);
+}
+
+// Host-pointer batch: bucket by device; per device copy in -> run -> copy out.
+// Frames are cut into chunks so that the H2D copy of chunk c+1 and the D2H copy
+// of chunk c-1 overlap the kernel of chunk c (three streams, events).
+int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
+              int16_t* out, size_t out_stride, int frames) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<Handle*> hs;
+  if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (frames == 0) return 0;
+  const int fl = (int)hs[0]->fs / 100;
+  // contiguous runs of batch indices that live on one device
+  struct Run { int dev, first, count; };
+  std::vector<Run> runs;
+  for (int i = 0; i < n; ++i) {
+    if (!runs.empty() && runs.back().dev == hs[i]->dev) runs.back().count++;
+    else runs.push_back(Run{hs[i]->dev, i, 1});
+  }
+  // chunking: aim at >= 4 chunks of >= 50 frames when there is enough work
+  int chunk = frames;
+  if (frames >= 200) chunk = (frames + 3) / 4;
+  if (chunk > 500) chunk = 500;
+  for (const Run& r : runs) {
+    DeviceCtx* d;
+    if (DeviceReady(r.dev, &d) != 0) return -1;
+    const size_t per = (size_t)chunk * fl;           // samples per stream per chunk
+    const size_t need = 2 * (size_t)r.count * per;   // double buffered
+    if (need > d->stage_elems) {
+      CU_OK(cudaDeviceSynchronize());
+      if (d->d_in) { CU_OK(cudaFree(d->d_in)); CU_OK(cudaFree(d->d_out)); }
+      CU_OK(cudaMalloc(&d->d_in, sizeof(int16_t) * need));
+      CU_OK(cudaMalloc(&d->d_out, sizeof(int16_t) * need));
+      d->stage_elems = need;
+    }
+  }
+  // One device at a time issues its whole pipeline asynchronously; devices run
+  // concurrently because nothing below blocks the host until the final syncs.
+  std::vector<std::vector<cudaEvent_t>> events(runs.size());
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    const Run& r = runs[ri];
+    DeviceCtx* d = &g_devs[r.dev];
+    CU_OK(cudaSetDevice(r.dev));
+    std::vector<Handle*> sub(hs.begin() + r.first, hs.begin() + r.first + r.count);
+    const size_t per = (size_t)chunk * fl;
+    const int nchunks = (frames + chunk - 1) / chunk;
+    std::vector<cudaEvent_t>& ev = events[ri];
+    ev.resize(3 * (size_t)nchunks);
+    for (auto& e : ev) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int c = 0; c < nchunks; ++c) {
+      const int f0 = c * chunk;
+      const int nf = frames - f0 < chunk ? frames - f0 : chunk;
+      int16_t* din = d->d_in + (size_t)(c & 1) * r.count * per;
+      int16_t* dout = d->d_out + (size_t)(c & 1) * r.count * per;
+      // buffer (c&1) was last read by kernel c-2 and last drained by copy-out c-2
+      if (c >= 2) {
+        CU_OK(cudaStreamWaitEvent(d->copy_in, ev[3 * (c - 2) + 1], 0));
+        CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * (c - 2) + 2], 0));
+      }
+      CU_OK(cudaMemcpy2DAsync(din, per * sizeof(int16_t), in + (size_t)r.first * in_stride + (size_t)f0 * fl,
+                              in_stride * sizeof(int16_t), (size_t)nf * fl * sizeof(int16_t), r.count,
+                              cudaMemcpyHostToDevice, d->copy_in));
+      CU_OK(cudaEventRecord(ev[3 * c + 0], d->copy_in));
+      CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * c + 0], 0));
+      if (RunDevice(*d, magic, sub, din, per, dout, per, nf, d->stream) != 0) return -1;
+      CU_OK(cudaEventRecord(ev[3 * c + 1], d->stream));
+      CU_OK(cudaStreamWaitEvent(d->copy_out, ev[3 * c + 1], 0));
+      CU_OK(cudaMemcpy2DAsync(out + (size_t)r.first * out_stride + (size_t)f0 * fl,
+                              out_stride * sizeof(int16_t), dout, per * sizeof(int16_t),
+                              (size_t)nf * fl * sizeof(int16_t), r.count, cudaMemcpyDeviceToHost, d->copy_out));
+      CU_OK(cudaEventRecord(ev[3 * c + 2], d->copy_out));
+    }
+  }
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    DeviceCtx* d = &g_devs[runs[ri].dev];
+    CU_OK(cudaSetDevice(runs[ri].dev));
+    CU_OK(cudaStreamSynchronize(d->copy_out));
+    CU_OK(cudaStreamSynchronize(d->stream));
+    for (auto& e : events[ri]) CU_OK(cudaEventDestroy(e));
+  }
+  return 0;
+}
+
+// Single-stream float call = batch of one over float band frames.
+int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_ss, float* out,
+                    size_t out_ss, int frames) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!hv || n <= 0) return Fail("no handles");
+  if (nb < 1 || nb > 3) return Fail("num_bands out of range");
+  std::vector<Handle*> hs(n);
+  for (int i = 0; i < n; ++i) {
+    Handle* h = AsHandle(hv[i], kMagicF);
+    if (!h) return Fail("bad handle in batch");
+    if (!h->init_flag) return Fail("handle not initialised");
+    if (h->fs != static_cast<Handle*>(hv[0])->fs || h->dev != static_cast<Handle*>(hv[0])->dev)
+      return Fail("mixed sample rates or devices in one batch");
+    hs[i] = h;
+  }
+  if (frames <= 0) return frames == 0 ? 0 : Fail("negative frame count");
+  const uint32_t fs = hs[0]->fs;
+  if (fs == 8000 && nb != 1) return Fail("8 kHz has a single band");
+  const int fl = fs == 8000 ? 80 : 160;
+  const int ana = fs == 8000 ? 128 : 256;
+  DeviceCtx* d;
+  if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
+  const size_t per = (size_t)frames * nb * fl;
+  float *din = nullptr, *dout = nullptr;
+  CU_OK(cudaMalloc(&din, sizeof(float) * per * n));
+  CU_OK(cudaMalloc(&dout, sizeof(float) * per * n));
+  int rc = 0;
+  do {
+    std::vector<int> slots(n);
+    for (int i = 0; i < n; ++i) slots[i] = hs[i]->slot;
+    if ((rc = UploadSlots(*d, slots, d->stream)) != 0) break;
+    cudaError_t e = cudaMemcpy2DAsync(din, per * sizeof(float), in, in_ss * sizeof(float), per * sizeof(float), n,
+                                      cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    NsfLaunch p;
+    p.state = (float*)d->f_state.base;
+    p.hist = (int*)d->f_hist.base;
+    p.slots = d->d_slots;
+    p.tables = d->d_nsf_tables;
+    p.in = din;
+    p.out = dout;
+    p.in_stream_stride = p.out_stream_stride = (long long)per;
+    p.in_frame_stride = p.out_frame_stride = (long long)nb * fl;
+    p.in_band_stride = p.out_band_stride = fl;
+    p.n_streams = n;
+    p.frames = frames;
+    if ((rc = LaunchNsf(ana, nb, false, p, d->stream)) != 0) break;
+    e = cudaMemcpy2DAsync(out, out_ss * sizeof(float), dout, per * sizeof(float), per * sizeof(float), n,
+                          cudaMemcpyDeviceToHost, d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+  } while (0);
+  cudaFree(din);
+  cudaFree(dout);
+  return rc;
+}
+
+__global__ void synth_kernel(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream,
+                             uint32_t fs, uint32_t first_sample, uint32_t n_samples, uint32_t seed) {
+  const size_t pairs = n_samples / 2;
+  const size_t total = (size_t)n_streams * pairs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t s = (uint32_t)(i / pairs);
+    const uint32_t n = (uint32_t)(i % pairs) * 2u;
+    const uint32_t a = (uint16_t)pcm_synth_sample(seed, first_stream + s, fs, first_sample + n);
+    const uint32_t b = (uint16_t)pcm_synth_sample(seed, first_stream + s, fs, first_sample + n + 1u);
+    reinterpret_cast<uint32_t*>(dst + (size_t)s * stride)[n / 2] = a | (b << 16);
+  }
+}
+
+__global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
+                                long long* sums) {
+  const int s = blockIdx.x;
+  if (s >= n_streams) return;
+  long long a = 0, b = 0;
+  const int16_t* p = pcm + (size_t)s * stride;
+  for (uint32_t i = threadIdx.x; i < n_samples; i += blockDim.x) {
+    const long long v = p[i];
+    a += v;
+    b += v * v;
+  }
+  __shared__ long long sa[256], sb[256];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sums[2 * s] = sa[0];
+    sums[2 * s + 1] = sb[0];
+  }
+}
+
+}  // namespace
+}  // namespace nsb200
+
+using namespace nsb200;
+
+extern "C" {
+
+int WebRtcNs_Create(NsHandle** h) { return Create(reinterpret_cast<void**>(h), kMagicF); }
+int WebRtcNs_Free(NsHandle* h) { return Free(h, kMagicF); }
+int WebRtcNs_Init(NsHandle* h, uint32_t fs) {
+  void* hv = h;
+  return InitMany(&hv, 1, fs, 0, kMagicF);
+}
+int WebRtcNs_set_policy(NsHandle* h, int mode) { return SetPolicy(h, mode, kMagicF); }
+
+void WebRtcNs_Analyze(NsHandle* hv, const float* spframe) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AsHandle(hv, kMagicF);
+  if (!h || !h->init_flag || !spframe) {
+    Fail("WebRtcNs_Analyze: handle not initialised");
+    return;
+  }
+  memcpy(h->analyze_frame, spframe, sizeof(float) * (h->fs == 8000 ? 80 : 160));
+  h->analyze_seen = true;
+}
+
+void WebRtcNs_Process(NsHandle* hv, const float* const* spframe, int num_bands, float* const* outframe) {
+  Handle* h = AsHandle(hv, kMagicF);
+  if (!h || !h->init_flag || !spframe || !outframe || num_bands < 1 || num_bands > 3) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Fail("WebRtcNs_Process: handle not initialised or bad arguments");
+    return;
+  }
+  const int fl = h->fs == 8000 ? 80 : 160;
+  float in[3 * 160], out[3 * 160];
+  for (int b = 0; b < num_bands; ++b) memcpy(in + b * fl, spframe[b], sizeof(float) * fl);
+  if (h->analyze_seen && memcmp(h->analyze_frame, in, sizeof(float) * fl) != 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err = "WebRtcNs_Process: band 0 differs from the frame given to WebRtcNs_Analyze; "
+            "statistics are taken from the Process frame (fused path)";
+  }
+  h->analyze_seen = false;
+  void* one = h;
+  if (ProcessBandsF32(&one, 1, num_bands, in, (size_t)num_bands * fl, out, (size_t)num_bands * fl, 1) != 0) return;
+  for (int b = 0; b < num_bands; ++b) memcpy(outframe[b], out + b * fl, sizeof(float) * fl);
+}
+
+float WebRtcNs_prior_speech_probability(NsHandle* hv) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AsHandle(hv, kMagicF);
+  if (!h || !h->init_flag) return -1.f;
+  DeviceCtx* d;
+  if (DeviceReady(h->dev, &d) != 0) return -1.f;
+  float v = -1.f;
+  cudaStreamSynchronize(d->stream);
+  if (cudaMemcpy(&v, (float*)d->f_state.base + (size_t)h->slot * kNsfStateWords + kH_priorSpeechProb,
+                 sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1.f;
+  return v;
+}
+
+int WebRtcNsx_Create(NsxHandle** h) { return Create(reinterpret_cast<void**>(h), kMagicX); }
+int WebRtcNsx_Free(NsxHandle* h) { return Free(h, kMagicX); }
+int WebRtcNsx_Init(NsxHandle* h, uint32_t fs) {
+  void* hv = h;
+  return InitMany(&hv, 1, fs, 0, kMagicX);
+}
+int WebRtcNsx_set_policy(NsxHandle* h, int mode) { return SetPolicy(h, mode, kMagicX); }
+
+void WebRtcNsx_Process(NsxHandle* hv, const short* const* speechFrame, int num_bands, short* const* outFrame) {
+  Handle* h = AsHandle(hv, kMagicX);
+  if (!h || !h->init_flag || !speechFrame || !outFrame || num_bands < 1 || num_bands > 3) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Fail("WebRtcNsx_Process: handle not initialised or bad arguments");
+    return;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int fl = h->fs == 8000 ? 80 : 160;
+  const int ana = h->fs == 8000 ? 128 : 256;
+  DeviceCtx* d;
+  if (DeviceReady(h->dev, &d) != 0) return;
+  int16_t buf[3 * 160];
+  for (int b = 0; b < num_bands; ++b) memcpy(buf + b * fl, speechFrame[b], sizeof(int16_t) * fl);
+  int16_t* dio = nullptr;
+  if (cudaMalloc(&dio, sizeof(buf)) != cudaSuccess) { Fail("cudaMalloc"); return; }
+  std::vector<int> slots(1, h->slot);
+  if (UploadSlots(*d, slots, d->stream) == 0 &&
+      cudaMemcpyAsync(dio, buf, sizeof(int16_t) * num_bands * fl, cudaMemcpyHostToDevice, d->stream) == cudaSuccess) {
+    NsxLaunch p;
+    p.state = (uint32_t*)d->x_state.base;
+    p.slots = d->d_slots;
+    p.tables = d->d_nsx_tables;
+    p.in = dio;
+    p.out = dio;
+    p.in_stream_stride = p.out_stream_stride = num_bands * fl;
+    p.in_frame_stride = p.out_frame_stride = num_bands * fl;
+    p.in_band_stride = p.out_band_stride = fl;
+    p.n_streams = 1;
+    p.frames = 1;
+    if (LaunchNsx(ana, num_bands, p, d->stream) == 0 &&
+        cudaMemcpyAsync(buf, dio, sizeof(int16_t) * num_bands * fl, cudaMemcpyDeviceToHost, d->stream) == cudaSuccess &&
+        cudaStreamSynchronize(d->stream) == cudaSuccess) {
+      for (int b = 0; b < num_bands; ++b) memcpy(outFrame[b], buf + b * fl, sizeof(int16_t) * fl);
+    } else {
+      Fail("WebRtcNsx_Process: launch or copy failed");
+    }
+  }
+  cudaFree(dio);
+}
+
+int WebRtcNs_ProcessBatch(NsHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os, int frames) {
+  return BatchHost(reinterpret_cast<void* const*>(hs), n, kMagicF, in, is, out, os, frames);
+}
+int WebRtcNsx_ProcessBatch(NsxHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os, int frames) {
+  return BatchHost(reinterpret_cast<void* const*>(hs), n, kMagicX, in, is, out, os, frames);
+}
+int WebRtcNs_ProcessBatchDevice(NsHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os,
+                                int frames, void* st) {
+  return BatchDevice(reinterpret_cast<void* const*>(hs), n, kMagicF, in, is, out, os, frames, st);
+}
+int WebRtcNsx_ProcessBatchDevice(NsxHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os,
+                                 int frames, void* st) {
+  return BatchDevice(reinterpret_cast<void* const*>(hs), n, kMagicX, in, is, out, os, frames, st);
+}
+int WebRtcNs_ProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* in, size_t is, float* out,
+                                  size_t os, int frames) {
+  return ProcessBandsF32(reinterpret_cast<void* const*>(hs), n, nb, in, is, out, os, frames);
+}
+int WebRtcNs_InitBatch(NsHandle* const* hs, int n, uint32_t fs, int mode) {
+  return InitMany(reinterpret_cast<void* const*>(hs), n, fs, mode, kMagicF);
+}
+int WebRtcNsx_InitBatch(NsxHandle* const* hs, int n, uint32_t fs, int mode) {
+  return InitMany(reinterpret_cast<void* const*>(hs), n, fs, mode, kMagicX);
+}
+
+int WebRtcNsB200_SetCreateDevice(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device >= 0) {
+    if (EnsureDevices() != 0) return -1;
+    if (device >= (int)g_devs.size()) return Fail("bad device index");
+  }
+  g_create_device = device;
+  return 0;
+}
+int WebRtcNsB200_DeviceCount(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (EnsureDevices() != 0) return 0;
+  return (int)g_devs.size();
+}
+int WebRtcNsB200_Synchronize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& d : g_devs) {
+    if (!d.ready) continue;
+    CU_OK(cudaSetDevice(d.dev));
+    CU_OK(cudaDeviceSynchronize());
+  }
+  return 0;
+}
+const char* WebRtcNsB200_LastError(void) { return g_err.c_str(); }
+uint64_t WebRtcNsB200_KernelLaunches(void) { return g_launches; }
+
+int WebRtcNsB200_SynthPcmDevice(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream, uint32_t fs,
+                                uint32_t first_sample, uint32_t n_samples, uint32_t seed, void* st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if ((stride & 1) || (n_samples & 1)) return Fail("stride and n_samples must be even");
+  synth_kernel<<<148 * 8, 256, 0, (cudaStream_t)st>>>(dst, stride, n_streams, first_stream, fs, first_sample,
+                                                     n_samples, seed);
+  ++g_launches;
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint32_t first_sample,
+                               uint32_t n_samples, uint32_t seed) {
+  for (uint32_t i = 0; i < n_samples; ++i) dst[i] = pcm_synth_sample(seed, stream, fs, first_sample + i);
+}
+int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
+                                int64_t* sums, void* st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums);
+  ++g_launches;
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Headline benchmark: NS audio-seconds per second over N streams (BASELINE.json metric).
+
+Workload (configs[1]): 4096 independent 16 kHz mono streams per GPU, float NS policy 2,
+synthetic PCM (csrc/pcm_synth.h, 8 stream classes).  One step = one WebRtcNs_ProcessBatch
+call walking F = --frames-per-step 10-ms frames of every stream; with the default
+--steps 60 and F = 100 the timed region is the configuration's full 60 s of audio.
+
+  value     PCM resident in HBM, WebRtcNs_ProcessBatchDevice, CUDA events on the launch stream
+  e2e       same steps through WebRtcNs_ProcessBatch with pinned HOST buffers
+            (H2D + kernels + D2H inside the timed region)
+  roofline  HBM: algorithmic bytes B(F) = IO + 2*S_hot/F per stream-frame
+  cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref) on the host cores
+
+N > 1: one process per GPU under torchrun, every rank owns its own 4096 streams (weak scaling,
+no data-path collective -- streams are independent); barrier + max over ranks for the time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_HOT = {("float", 16000): 7120, ("float", 8000): 3664, ("float", 48000): 8448, ("float", 32000): 7888,
+         ("fixed", 16000): 4414, ("fixed", 8000): 2302, ("fixed", 32000): 5182, ("fixed", 48000): 5742}
+
+
+def algorithmic_bytes(kind, fs, frames_per_launch):
+    io = 2 * 2 * (fs // 100)            # int16 in + int16 out per stream-frame
+    return io + 2.0 * S_HOT[(kind, fs)] / frames_per_launch
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in o.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def ref_lib():
+    path = os.path.join(ROOT, "oracle", "_ref", "libns_ref.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_run_mt.restype = C.c_double
+    return lib
+
+
+def cpu_reference_run(kind, fs, mode, streams, frames, threads):
+    """Times the unmodified reference (oracle/_ref) on `threads` host threads; returns audio-s/s."""
+    import numpy as np
+    import audiosignalprocess_b200 as pkg
+    lib = ref_lib()
+    if lib is None:
+        return None
+    fl = fs // 100
+    x = pkg.synth_pcm_host(streams, fs, frames * fl)
+    out = np.zeros_like(x)
+    sec = lib.ref_run_mt(1 if kind == "fixed" else 0, fs, mode, streams, frames, threads,
+                         x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return streams * frames * 0.01 / sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--fs", type=int, default=16000)
+    ap.add_argument("--mode", type=int, default=2)
+    ap.add_argument("--fixed", action="store_true", help="WebRtcNsx (fixed point) instead of float NS")
+    ap.add_argument("--frames-per-step", type=int, default=100)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kind = "fixed" if a.fixed else "float"
+    F = a.frames_per_step
+    fl = a.fs // 100
+    workload = "%d independent %d Hz mono streams/GPU, %s policy %d, F=%d frames per launch (%.1f s of audio per step)" % (
+        a.streams, a.fs, "WebRtcNsx fixed" if a.fixed else "WebRtcNs float", a.mode, F, F * 0.01)
+    config = {"workload": workload, "streams_per_gpu": a.streams, "fs": a.fs, "policy": a.mode,
+              "frames_per_launch": F, "pcm": "int16",
+              "l2": "every step streams fresh PCM (in+out %.0f MB per step) larger than the 126 MB L2" % (
+                  2 * a.streams * F * fl * 2 / 1e6)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        # bounded sample of the same workload: cores*8 streams, F frames per step
+        streams = min(a.streams, cores * 8)
+        for _ in range(min(a.warmup, 1)):
+            cpu_reference_run(kind, a.fs, a.mode, streams, F, cores)
+        t0 = time.time()
+        vals = []
+        for _ in range(a.steps):
+            v = cpu_reference_run(kind, a.fs, a.mode, streams, F, cores)
+            if v is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libns_ref.so missing"}))
+                return 0
+            vals.append(v)
+            if time.time() - t0 > 120:
+                break
+        value = len(vals) / sum(1.0 / v for v in vals)
+        sample = "%d streams x %d frames per step, %d steps, reference C (gcc -O2), %d pthreads" % (
+            streams, F, len(vals), cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "ns_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+            "n_gpus": a.gpus, "steps": len(vals), "warmup": min(a.warmup, 1),
+            "ms_per_step": 1e3 * streams * F * 0.01 / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if not a.fixed else "int16/int32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import audiosignalprocess_b200 as pkg
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = pkg.load_library()
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total_steps = a.warmup + a.steps
+    n_samples = total_steps * F * fl
+    pcm_in = torch.empty((a.streams, n_samples), dtype=torch.int16, device=dev)
+    pcm_out = torch.empty_like(pcm_in)
+    stream = torch.cuda.current_stream()
+    rc = lib.WebRtcNsB200_SynthPcmDevice(C.c_void_p(pcm_in.data_ptr()), n_samples, a.streams, rank * a.streams,
+                                         a.fs, 0, n_samples, 1234, C.c_void_p(stream.cuda_stream))
+    assert rc == 0, lib.WebRtcNsB200_LastError()
+    torch.cuda.synchronize()
+    batch = pkg.NsBatch(a.streams, a.fs, a.mode, fixed=a.fixed, devices=[local_rank])
+
+    def step_device(i):
+        off = i * F * fl * 2
+        batch.process_device(pcm_in.data_ptr() + off, n_samples, pcm_out.data_ptr() + off, n_samples, F,
+                             stream.cuda_stream)
+
+    for i in range(a.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.WebRtcNsB200_KernelLaunches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record(stream)
+    for i in range(a.steps):
+        step_device(a.warmup + i)
+        ev[i + 1].record(stream)
+    barrier()
+    launches = lib.WebRtcNsB200_KernelLaunches() - launches0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    audio_s = a.streams * a.steps * F * 0.01 * world
+    value = audio_s / (ms_total_max * 1e-3)
+
+    # ---- end to end through the host-pointer C call, pinned buffers
+    e2e = None
+    if not a.no_e2e:
+        e_steps = a.steps
+        host_in = torch.empty((a.streams, F * fl), dtype=torch.int16).pin_memory()
+        host_out = torch.empty((a.streams, F * fl), dtype=torch.int16).pin_memory()
+        host_in.copy_(pcm_in[:, :F * fl].cpu())
+        batch.reset(a.mode)
+        for _ in range(a.warmup):
+            batch.process_ptr(host_in.data_ptr(), F * fl, host_out.data_ptr(), F * fl, F)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            batch.process_ptr(host_in.data_ptr(), F * fl, host_out.data_ptr(), F * fl, F)
+            _ = int(host_out[0, 0])   # the step's result is read on the host
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": a.streams * e_steps * F * 0.01 * world / float(t.item()), "unit": "audio-s/s",
+               "h2d_bytes_per_step": a.streams * F * fl * 2, "d2h_bytes_per_step": a.streams * F * fl * 2}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, which = measured_peak_gbs()
+        bytes_per_sf = algorithmic_bytes(kind, a.fs, F)
+        med = sorted(step_ms)[len(step_ms) // 2]
+        avg_ms = ms_total / a.steps      # rank 0's own launches
+        achieved = bytes_per_sf * a.streams * F / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": which, "kernel": "nsx_process_kernel" if a.fixed else "nsf_process_kernel",
+                    "bytes_per_stream_frame": bytes_per_sf, "frames_per_launch": F,
+                    "launch_ms_avg": avg_ms, "launch_ms_median": med}
+        cpu = None
+        if not a.no_cpu:
+            cores = os.cpu_count() or 1
+            streams = cores * 8
+            frames = 1000
+            v = cpu_reference_run(kind, a.fs, a.mode, streams, frames, cores)
+            if v is not None:
+                cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+                       "sample": "%d streams x %d frames (%.0f s of audio each), %d pthreads, one stream per core at a time"
+                                 % (streams, frames, frames * 0.01, cores)}
+        line = {"metric": "ns_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total_max / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32" if a.fixed else "f32",
+                "data": "synthetic", "config": config, "clocks": sampler.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,132 @@
+"""GPU parity of the float suppressor (WebRtcNs_*) against the compiled reference.
+
+Tolerance (BASELINE.json north_star): max abs error <= 1e-4 full scale (3.2768 in int16
+units) and SNR of the difference >= 90 dB per stream; prior speech probability within 5e-4
+(the tolerance the reference's own ApmTest uses, audio_processing_unittest.cc:2056)."""
+import numpy as np
+import pytest
+
+from conftest import snr_db
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-4 * 32768.0
+MIN_SNR = 90.0
+
+
+def _check(ref, out, what):
+    err = np.abs(out.astype(np.float64) - ref.astype(np.float64)).max()
+    snr = snr_db(ref, out)
+    assert err <= MAX_ABS, "%s: max abs %.4f" % (what, err)
+    assert snr >= MIN_SNR or float(np.abs(ref).max()) == 0.0, "%s: snr %.1f dB" % (what, snr)
+    return err, snr
+
+
+@pytest.mark.parametrize("fs,mode,frames", [(16000, 2, 1200), (16000, 0, 300), (16000, 1, 300),
+                                            (16000, 3, 300), (8000, 2, 1200), (8000, 1, 300)])
+def test_batch_int16_all_stream_classes(nslib, reflib, fs, mode, frames):
+    """8 synthetic stream classes (noise, tones, chirps, digital silence, clipping, delayed
+    start) through WebRtcNs_ProcessBatch in ragged chunk sizes; >= 2 threshold windows at 1200."""
+    n = 8
+    fl = fs // 100
+    x = nslib.synth_pcm_host(n, fs, frames * fl)
+    b = nslib.NsBatch(n, fs, mode)
+    out = np.zeros_like(x)
+    f0 = 0
+    for chunk in [1, 2, 7, 40, 250, 10 ** 9]:   # F = frames per launch varies; state round-trips HBM
+        nf = min(chunk, frames - f0)
+        if nf <= 0:
+            break
+        out[:, f0 * fl:(f0 + nf) * fl] = b.process(x[:, f0 * fl:(f0 + nf) * fl])
+        f0 += nf
+    for s in range(n):
+        _, refi, pp = reflib.ns(fs, mode, x[s])
+        # int16 output: the float error bound plus one rounding step
+        err = np.abs(out[s].astype(np.int32) - refi.astype(np.int32)).max()
+        assert err <= 4, "stream %d: int16 diff %d" % (s, err)
+        assert snr_db(refi, out[s]) >= 60.0 or np.abs(refi).max() == 0
+        assert abs(b.prior_speech_probability(s) - pp[-1]) <= 5e-4
+    b.close()
+
+
+@pytest.mark.parametrize("fs,mode", [(16000, 2), (8000, 2), (16000, 0)])
+def test_batch_float_bands_parity(nslib, reflib, fs, mode):
+    """Float in / float out (the WebRtcNs_Process ABI, batched): the stated tolerance."""
+    n, frames = 8, 1100
+    fl = fs // 100
+    x = nslib.synth_pcm_host(n, fs, frames * fl)
+    b = nslib.NsBatch(n, fs, mode)
+    xin = x.astype(np.float32).reshape(n, frames, 1, fl)
+    out = b.process_bands_f32(xin).reshape(n, frames * fl)
+    worst = (0.0, 999.0)
+    for s in range(n):
+        reff, _, pp = reflib.ns(fs, mode, x[s])
+        err, snr = _check(reff, out[s], "stream %d" % s)
+        worst = (max(worst[0], err), min(worst[1], snr))
+        assert abs(b.prior_speech_probability(s) - pp[-1]) <= 5e-4
+    print("float parity fs=%d mode=%d: worst max-abs %.4f, worst snr %.1f dB" % (fs, mode, worst[0], worst[1]))
+    b.close()
+
+
+def test_single_stream_api_matches_reference(nslib, reflib):
+    """Create/Init/set_policy/Analyze/Process/prior_speech_probability frame by frame,
+    in place (outframe aliases spframe in the reference callers)."""
+    fs, mode, frames = 16000, 2, 120
+    x = nslib.synth_pcm_host(3, fs, frames * 160)[2]
+    ns = nslib.NoiseSuppressor()
+    assert ns.init(fs) == 0
+    assert ns.set_policy(mode) == 0
+    reff, _, pp = reflib.ns(fs, mode, x)
+    out = np.zeros(frames * 160, np.float32)
+    for f in range(frames):
+        fr = x[f * 160:(f + 1) * 160].astype(np.float32)
+        ns.analyze(fr)
+        out[f * 160:(f + 1) * 160] = ns.process([fr])[0]
+        if f % 40 == 0:
+            assert abs(ns.prior_speech_probability() - pp[f]) <= 5e-4
+    _check(reff, out, "single stream")
+    ns.free()
+
+
+def test_error_behaviour_matches_reference(nslib):
+    """ns_core.c:77-86 (fs), :1015-1017 (mode), noise_suppression.c:57-64 (getter)."""
+    ns = nslib.NoiseSuppressor()
+    assert ns.prior_speech_probability() == -1.0      # not initialised
+    assert ns.init(44100) == -1
+    assert ns.init(16000) == 0
+    assert ns.set_policy(4) == -1
+    assert ns.set_policy(-1) == -1
+    assert ns.set_policy(3) == 0
+    assert ns.prior_speech_probability() == pytest.approx(0.5)
+    assert ns.init(8000) == 0                          # re-Init on a live handle is allowed
+    ns.free()
+    lib = nslib.load_library()
+    assert lib.WebRtcNs_Free(None) == 0
+    assert lib.WebRtcNs_Init(None, 16000) == -1
+    assert lib.WebRtcNs_prior_speech_probability(None) == -1.0
+
+
+def test_reinit_resets_state(nslib, reflib):
+    fs, mode, frames = 16000, 2, 150
+    x = nslib.synth_pcm_host(2, fs, frames * 160)
+    b = nslib.NsBatch(2, fs, mode)
+    first = b.process(x)
+    b.reset(mode)
+    again = b.process(x)
+    assert np.array_equal(first, again)
+    b.close()
+
+
+def test_slot_reuse_and_many_handles(nslib, reflib):
+    """Free/Create cycles reuse slab slots; a pool growth (>1024 handles) keeps live state."""
+    fs, mode, frames = 16000, 2, 60
+    x = nslib.synth_pcm_host(1, fs, 2 * frames * 160)
+    a = nslib.NsBatch(1, fs, mode)
+    o1 = a.process(x[:, :frames * 160])
+    big = nslib.NsBatch(1500, fs, mode)        # forces the slab pool to grow and move
+    o2 = a.process(x[:, frames * 160:])
+    big.close()
+    _, refi, _ = reflib.ns(fs, mode, x[0])
+    got = np.concatenate([o1[0], o2[0]])
+    assert np.abs(got.astype(np.int32) - refi.astype(np.int32)).max() <= 4
+    a.close()
