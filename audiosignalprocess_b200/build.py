@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libwebrtc_ns_b200.so")
 SRC = os.path.join(HERE, "csrc", "ns_capi.cu")
 NVCC_FLAGS = [
-    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-std=c++17", "-O3", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-enum-compare",
 ]
 

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwebrtc_ns_b200.so")
+# NSB200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("NSB200_LIB") or os.path.join(HERE, "libwebrtc_ns_b200.so")
 
 # every symbol include/webrtc_ns_b200.h declares: (restype, argtypes)
 _H = C.c_void_p

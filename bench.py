@@ -181,7 +181,10 @@ def main():
     n_samples = total_steps * F * fl
     pcm_in = torch.empty((a.streams, n_samples), dtype=torch.int16, device=dev)
     pcm_out = torch.empty_like(pcm_in)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library treats NULL as "use my own stream", and the
+    # timing events must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     rc = lib.WebRtcNsB200_SynthPcmDevice(C.c_void_p(pcm_in.data_ptr()), n_samples, a.streams, rank * a.streams,
                                          a.fs, 0, n_samples, 1234, C.c_void_p(stream.cuda_stream))
     assert rc == 0, lib.WebRtcNsB200_LastError()
