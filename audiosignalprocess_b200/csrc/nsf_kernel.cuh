@@ -29,7 +29,10 @@
 
 namespace nsb200 {
 
-constexpr int kNsfWarpsPerCta = 4;
+// 2-warp CTAs, 7 per SM (<= 146 registers): 14 resident streams per SM, so that the
+// headline 4096-stream batch is exactly two balanced rounds over 148 SMs.
+constexpr int kNsfWarpsPerCta = 2;
+constexpr int kNsfCtasPerSm = 7;
 constexpr int kNsfCtaTableWords = 912;  // win 256 | tw 512 | logi 132 | pad
 constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
 
@@ -159,7 +162,7 @@ NSB_DEV void nsf_extract_params(float* H, int* hist, int lane) {
 // I16: PCM is int16 (rounded on output like IFChannelBuffer::RefreshI,
 // channel_buffer.cc:55-60) or float in int16 scale (the WebRtcNs_Process ABI).
 template <int ANA, int NB, bool I16>
-__global__ void __launch_bounds__(kNsfWarpsPerCta * 32)
+__global__ void __launch_bounds__(kNsfWarpsPerCta * 32, kNsfCtasPerSm)
 nsf_process_kernel(const NsfLaunch p) {
   typedef NsfGeo<ANA> G;
   extern __shared__ float4 nsf_smem4[];
