@@ -1,0 +1,31 @@
+/* TEST INFRASTRUCTURE ONLY.  Public face of liboracle_ns.so: a scalar CPU
+ * restatement of the reference's noise-suppression path, used by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg as the checker --
+ * never by the product. */
+#ifndef ORACLE_NS_ORACLE_H_
+#define ORACLE_NS_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- fixed-point suppressor (WebRtcNsx_*) ---- */
+typedef struct NsxOracle NsxOracle;
+NsxOracle* nsx_oracle_create(void);
+void nsx_oracle_free(NsxOracle* s);
+int nsx_oracle_init(NsxOracle* s, uint32_t fs);                 /* 0 / -1 */
+int nsx_oracle_set_policy(NsxOracle* s, int mode);              /* 0 / -1 */
+void nsx_oracle_process(NsxOracle* s, const int16_t* const* in, int num_bands, int16_t* const* out);
+/* one stream, 8/16 kHz, nframes frames of fs/100 samples */
+int nsx_oracle_run(int fs, int mode, int nframes, const int16_t* pcm_in, int16_t* pcm_out);
+/* primitives for known-answer tests */
+int nsx_oracle_real_fft(int order, int inverse, const int16_t* in, int16_t* out);
+const int16_t* nsx_oracle_table(const char* name, int* len);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ORACLE_NS_ORACLE_H_ */
