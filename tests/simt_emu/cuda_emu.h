@@ -105,5 +105,10 @@ template <typename T> inline T __ldcg(const T* p) { return *p; }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline unsigned __brev(unsigned x) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+  return r;
+}
 
 #endif  // TESTS_SIMT_EMU_CUDA_EMU_H_
