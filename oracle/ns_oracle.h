@@ -11,6 +11,18 @@
 extern "C" {
 #endif
 
+/* ---- float suppressor (WebRtcNs_*) ---- */
+typedef struct NsfOracle NsfOracle;
+NsfOracle* nsf_oracle_create(void);
+void nsf_oracle_free(NsfOracle* s);
+int nsf_oracle_init(NsfOracle* s, uint32_t fs);                 /* 0 / -1 */
+int nsf_oracle_set_policy(NsfOracle* s, int mode);              /* 0 / -1 */
+void nsf_oracle_analyze(NsfOracle* s, const float* frame);
+void nsf_oracle_process(NsfOracle* s, const float* const* in, int num_bands, float* const* out);
+float nsf_oracle_prior_speech_probability(const NsfOracle* s);  /* -1 when uninitialised */
+/* one stream, 8/16 kHz: Analyze + Process per frame; out_f32 in int16 scale */
+int nsf_oracle_run(int fs, int mode, int nframes, const int16_t* pcm_in, float* out_f32, float* prior_prob);
+
 /* ---- fixed-point suppressor (WebRtcNsx_*) ---- */
 typedef struct NsxOracle NsxOracle;
 NsxOracle* nsx_oracle_create(void);
