@@ -674,6 +674,31 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
   return rc;
 }
 
+// Device self-test of the arithmetic shortcuts: fdiv() against IEEE division and
+// fx_sqrt_floor() against the reference's restoring iteration (spl_sqrt_floor.c:55),
+// over pseudo-random operands in the kernels' ranges.  Counts mismatches.
+__global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned long long* bad) {
+  unsigned long long mism = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t h1 = pcm_mix32(seed + (uint32_t)i * 2u + (uint32_t)(i >> 31));
+    const uint32_t h2 = pcm_mix32(h1 ^ 0x9E3779B9u);
+    // floats with exponents in [2^-20, 2^40): sign from the hash
+    const float a = __uint_as_float((h1 & 0x807fffffu) | (((h1 >> 23) % 60u + 107u) << 23));
+    const float b = __uint_as_float((h2 & 0x007fffffu) | (((h2 >> 23) % 60u + 107u) << 23));
+    if (__float_as_uint(fdiv(a, b)) != __float_as_uint(__fdiv_rn(a, b))) ++mism;
+    const float c = (float)(h1 % 401u);   // small integers as in counters
+    if (__float_as_uint(fdiv(c, (float)(h2 % 200u + 1u))) != __float_as_uint(__fdiv_rn(c, (float)(h2 % 200u + 1u)))) ++mism;
+    int32_t v = (int32_t)h2, root = 0;
+    for (int k = 15; k >= 0; --k) {
+      const int32_t t = root + (1 << k);
+      if (v >= (int32_t)((uint32_t)t << k)) { v -= (int32_t)((uint32_t)t << k); root |= 2 << k; }
+    }
+    if ((uint32_t)(root >> 1) != fx_sqrt_floor(h2)) ++mism;
+  }
+  if (mism) atomicAdd(bad, mism);
+}
+
 __global__ void synth_kernel(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream,
                              uint32_t fs, uint32_t first_sample, uint32_t n_samples, uint32_t seed) {
   const size_t pairs = n_samples / 2;
@@ -875,6 +900,26 @@ int WebRtcNsB200_Synchronize(void) {
 }
 const char* WebRtcNsB200_LastError(void) { return g_err.c_str(); }
 uint64_t WebRtcNsB200_KernelLaunches(void) { return g_launches; }
+
+int WebRtcNsB200_SelfTest(uint64_t n_cases) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = 0;
+  if (EnsureDevices() != 0) return -1;
+  cudaGetDevice(&dev);
+  DeviceCtx* d;
+  if (DeviceReady(dev, &d) != 0) return -1;
+  unsigned long long* bad = nullptr;
+  CU_OK(cudaMalloc(&bad, sizeof(*bad)));
+  CU_OK(cudaMemsetAsync(bad, 0, sizeof(*bad), d->stream));
+  selftest_kernel<<<148 * 4, 256, 0, d->stream>>>(n_cases, 12345u, bad);
+  ++g_launches;
+  unsigned long long h = 0;
+  CU_OK(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
+  CU_OK(cudaStreamSynchronize(d->stream));
+  cudaFree(bad);
+  if (h != 0) return Fail("self-test: " + std::to_string(h) + " arithmetic mismatches");
+  return 0;
+}
 
 int WebRtcNsB200_SynthPcmDevice(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream, uint32_t fs,
                                 uint32_t first_sample, uint32_t n_samples, uint32_t seed, void* st) {

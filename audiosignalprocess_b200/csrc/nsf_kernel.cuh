@@ -380,11 +380,11 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           const float c1 = (float)(cnt[s] + 1);
-          const float delta = dn[s] > 1.f ? 40.f / dn[s] : 40.f;
-          if (lmagn[j] > lq[s]) lq[s] += 0.25f * delta / c1;
-          else lq[s] -= (1.f - 0.25f) * delta / c1;
+          const float delta = dn[s] > 1.f ? fdiv(40.f, dn[s]) : 40.f;
+          if (lmagn[j] > lq[s]) lq[s] += fdiv(0.25f * delta, c1);
+          else lq[s] -= fdiv((1.f - 0.25f) * delta, c1);
           if (fabsf(lmagn[j] - lq[s]) < 0.01f)
-            dn[s] = ((float)cnt[s] * dn[s] + 1.f / (2.f * 0.01f)) / c1;
+            dn[s] = fdiv((float)cnt[s] * dn[s] + 1.f / (2.f * 0.01f), c1);
           if (latch[s] && updates >= 200) quant = expf(lq[s]);
         }
         if (updates < 200) quant = expf(lq[2]);
@@ -474,9 +474,9 @@ nsf_process_kernel(const NsfLaunch p) {
         noisePrev[j] = r2.x;
         logLrt[j] = r2.z;
         mpause[j] = r2.w;
-        prevEst[j] = r2.y / (r2.x + 0.0001f) * smooth;
+        prevEst[j] = fdiv(r2.y, r2.x + 0.0001f) * smooth;
         snrPost[j] = 0.f;
-        if (magn[j] > noise[j]) snrPost[j] = magn[j] / (noise[j] + 0.0001f) - 1.f;
+        if (magn[j] > noise[j]) snrPost[j] = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
         snrPrior[j] = 0.98f * prevEst[j] + (1.f - 0.98f) * snrPost[j];
         if (!nyq || lane == 0) {
           sumPause += mpause[j];
@@ -559,7 +559,7 @@ nsf_process_kernel(const NsfLaunch p) {
         for (int j = 0; j < G::kSlots; ++j) {
           const bool nyq = (j == G::kSlots - 1);
           const float t1 = 1.f + 2.f * snrPrior[j];
-          const float t2 = 2.f * snrPrior[j] / (t1 + 0.0001f);
+          const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
           const float bessel = (snrPost[j] + 1.f) * t2;
           logLrt[j] += 0.5f * (bessel - logf(t1) - logLrt[j]);
           if (!nyq || lane == 0) lsum += logLrt[j];
@@ -592,7 +592,7 @@ nsf_process_kernel(const NsfLaunch p) {
         for (int j = 0; j < G::kSlots; ++j) {
           float inv = expf(-logLrt[j]);
           inv = gainPrior * inv;
-          prob[j] = 1.f / (1.f + inv);
+          prob[j] = fdiv(1.f, 1.f + inv);
         }
       }
 
@@ -632,9 +632,9 @@ nsf_process_kernel(const NsfLaunch p) {
         const bool nyq = (j == G::kSlots - 1);
         const int k = nyq ? G::kNC : lane + 32 * j;
         float cur_est = 0.f;
-        if (magn[j] > noise[j]) cur_est = magn[j] / (noise[j] + 0.0001f) - 1.f;
+        if (magn[j] > noise[j]) cur_est = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
         const float sp = 0.98f * prevEst[j] + (1.f - 0.98f) * cur_est;
-        float flt = sp / (overdrive + sp);
+        float flt = fdiv(sp, overdrive + sp);
         if (flt < denoiseBound) flt = denoiseBound;
         if (flt > 1.f) flt = 1.f;
         if (blockInd < 50) {

@@ -113,6 +113,9 @@ int WebRtcNsB200_Synchronize(void);
 const char* WebRtcNsB200_LastError(void);
 /* Kernels launched by this library since load (for bench.py's gpu_launches). */
 uint64_t WebRtcNsB200_KernelLaunches(void);
+/* Device self-test of the kernels' arithmetic shortcuts (branch-free IEEE division, floor
+ * square root) against their exact definitions over n_cases operands.  0 = all identical. */
+int WebRtcNsB200_SelfTest(uint64_t n_cases);
 /* Deterministic synthetic PCM (csrc/pcm_synth.h) written on the device:
  * stream s, sample n -> dst[s*stride + n], n < n_samples, as stream index
  * first_stream + s at time offset first_sample. */

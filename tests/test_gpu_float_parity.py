@@ -134,3 +134,9 @@ def test_slot_reuse_and_many_handles(nslib, reflib):
     got = np.concatenate([o1[0], o2[0]])
     assert judge_float(refi, got, slack=1.0)[0]
     a.close()
+
+
+def test_device_arithmetic_selftest(nslib):
+    """fdiv() == IEEE division and fx_sqrt_floor() == WebRtcSpl_SqrtFloor, bit for bit, 2^28 cases."""
+    lib = nslib.load_library()
+    assert lib.WebRtcNsB200_SelfTest(1 << 28) == 0, lib.WebRtcNsB200_LastError()
