@@ -19,6 +19,7 @@
 #include "nsf_kernel.cuh"
 #include "nsx_host_init.h"
 #include "nsx_kernel.cuh"
+#include "band_host_init.h"
 #include "band_kernels.cuh"
 #include "pcm_synth.h"
 
@@ -70,6 +71,8 @@ struct DeviceCtx {
   cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
   NsfTables* d_nsf_tables = nullptr;
   NsxTables* d_nsx_tables = nullptr;
+  float* d_sinc_up = nullptr;     // 33 x 32 taps, 480 -> 640
+  float* d_sinc_down = nullptr;   // 33 x 32 taps, 640 -> 480
   SlabPool f_state, f_hist, x_state, b_state;  // float state, float histograms, fixed state, band-split state
   void* d_template = nullptr;   // scratch for Init templates
   size_t template_bytes = 0;
@@ -83,6 +86,8 @@ struct DeviceCtx {
   size_t stage_elems = 0;
   int16_t* d_bands = nullptr;   // [stream][frame][band][160] scratch for 32/48 kHz
   size_t bands_elems = 0;
+  int16_t* d_band_scratch = nullptr;   // 48 kHz: 64 kHz and 32 kHz intermediates
+  size_t band_scratch_elems = 0;
 };
 
 std::vector<DeviceCtx> g_devs;
@@ -147,6 +152,15 @@ int DeviceReady(int dev, DeviceCtx** out) {
       CU_OK(cudaMalloc(&d.d_nsx_tables, sizeof(NsxTables)));
       CU_OK(cudaMemcpy(d.d_nsx_tables, t, sizeof(NsxTables), cudaMemcpyHostToDevice));
       delete t;
+    }
+    {
+      std::vector<float> k(33 * 32);
+      band_make_sinc_kernel(480.0 / 640.0, k.data());
+      CU_OK(cudaMalloc(&d.d_sinc_up, sizeof(float) * k.size()));
+      CU_OK(cudaMemcpy(d.d_sinc_up, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice));
+      band_make_sinc_kernel(640.0 / 480.0, k.data());
+      CU_OK(cudaMalloc(&d.d_sinc_down, sizeof(float) * k.size()));
+      CU_OK(cudaMemcpy(d.d_sinc_down, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice));
     }
     d.f_state.slab_bytes = sizeof(uint32_t) * kNsfStateWords;
     d.f_hist.slab_bytes = sizeof(uint32_t) * kNsfHistWords;
@@ -311,9 +325,14 @@ int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
                                                  nullptr, 0, nullptr, 0);
     }
     ++g_launches;
-    // band-split state: zero (TwoBandsStates ctor, splitting_filter.h:34-39; resampler priming)
+    // band-split state: zero filter states (TwoBandsStates ctor, splitting_filter.h:34-39),
+    // resamplers as their zero-primed first pass leaves them
     if (UploadSlots(*d, bslots, d->stream) != 0) return -1;
-    CU_OK(cudaMemsetAsync(d->d_template, 0, d->template_bytes, d->stream));
+    {
+      std::vector<uint32_t> bt(kBandStateWords);
+      band_init_state(bt.data());
+      CU_OK(cudaMemcpyAsync(d->d_template, bt.data(), sizeof(uint32_t) * kBandStateWords, cudaMemcpyHostToDevice, d->stream));
+    }
     slab_fill_kernel<<<m, 256, 0, d->stream>>>((uint32_t*)d->b_state.base, kBandStateWords,
                                                (const uint32_t*)d->d_template, d->d_slots, m,
                                                nullptr, 0, nullptr, 0);
@@ -435,6 +454,14 @@ int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, cons
       CU_OK(cudaMalloc(&d.d_bands, sizeof(int16_t) * need));
       d.bands_elems = need;
     }
+    const size_t need_s = BandScratchElems(nb, n, frames);
+    if (need_s > d.band_scratch_elems) {
+      CU_OK(cudaStreamSynchronize(st));
+      if (d.d_band_scratch) CU_OK(cudaFree(d.d_band_scratch));
+      CU_OK(cudaMalloc(&d.d_band_scratch, sizeof(int16_t) * need_s));
+      d.band_scratch_elems = need_s;
+    }
+    if ((in_stride | out_stride) & 7) return Fail("strides must be multiples of 8 samples at 32/48 kHz");
     ns_in = ns_out = d.d_bands;
     ns_in_ss = ns_out_ss = (long long)frames * nb * 160;
     fstride = nb * 160;
@@ -456,6 +483,9 @@ int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, cons
     b.bands_stride = ns_in_ss;
     b.n_streams = n;
     b.frames = frames;
+    b.kernel_up = d.d_sinc_up;
+    b.kernel_down = d.d_sinc_down;
+    b.scratch = d.d_band_scratch;
     if (LaunchBandSplit(nb, b, st, &g_launches) != 0) return Fail("band split launch failed");
   }
   if (magic == kMagicF) {
@@ -498,6 +528,9 @@ int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, cons
     b.bands_stride = ns_in_ss;
     b.n_streams = n;
     b.frames = frames;
+    b.kernel_up = d.d_sinc_up;
+    b.kernel_down = d.d_sinc_down;
+    b.scratch = d.d_band_scratch;
     if (LaunchBandMerge(nb, b, st, &g_launches) != 0) return Fail("band merge launch failed");
   }
   return 0;
@@ -552,10 +585,11 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     if (!runs.empty() && runs.back().dev == hs[i]->dev) runs.back().count++;
     else runs.push_back(Run{hs[i]->dev, i, 1});
   }
-  // chunking: aim at >= 4 chunks of >= 50 frames when there is enough work
+  // chunking: >= 4 chunks when there is enough work, so that copy-in, kernel and
+  // copy-out of neighbouring chunks overlap (PCIe is full duplex)
   int chunk = frames;
-  if (frames >= 200) chunk = (frames + 3) / 4;
-  if (chunk > 500) chunk = 500;
+  if (frames >= 16) chunk = (frames + 3) / 4;
+  if (chunk > 250) chunk = 250;
   for (const Run& r : runs) {
     DeviceCtx* d;
     if (DeviceReady(r.dev, &d) != 0) return -1;
