@@ -36,6 +36,19 @@ int nsx_oracle_run(int fs, int mode, int nframes, const int16_t* pcm_in, int16_t
 int nsx_oracle_real_fft(int order, int inverse, const int16_t* in, int16_t* out);
 const int16_t* nsx_oracle_table(const char* name, int* len);
 
+/* ---- 32/48 kHz band split / merge (AudioBuffer + SplittingFilter) ---- */
+typedef struct BandOracle BandOracle;
+BandOracle* band_oracle_create(int fs);
+void band_oracle_free(BandOracle* b);
+int band_oracle_num_bands(const BandOracle* b);
+void band_oracle_split(BandOracle* b, const int16_t* in, int16_t* bands);   /* bands [nb][160] */
+void band_oracle_merge(BandOracle* b, const int16_t* bands, int16_t* out);
+void band_oracle_qmf_analysis(const int16_t* in, int len, int16_t* low, int16_t* high, int32_t* st1, int32_t* st2);
+void band_oracle_qmf_synthesis(const int16_t* low, const int16_t* high, int band_len, int16_t* out,
+                               int32_t* st1, int32_t* st2);
+/* whole path for one stream at any supported rate: split -> NSx (fixed=1) / float NS -> merge */
+int band_oracle_run(int fixed, int fs, int mode, int nframes, const int16_t* pcm_in, int16_t* pcm_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,3 +57,23 @@ extern "C" int emu_nsx_run(int fs, int mode, int nb, int nstreams, int nframes, 
   }
   return 0;
 }
+
+// Dumps the product's NSx tables (nsx_host_init.h) for tests/test_tables.py.
+extern "C" void emu_nsx_tables(int16_t* win256, int16_t* win128, uint32_t* tw, int16_t* log_frac,
+                               int16_t* counter_div, int16_t* log_tab, int16_t* log_idx, int16_t* factor1,
+                               int16_t* factor2, int16_t* indicator, int16_t* misc5) {
+  nsb200::NsxTables t;
+  nsb200::nsx_fill_tables(&t);
+  memcpy(win256, t.win256, sizeof(t.win256));
+  memcpy(win128, t.win128, sizeof(t.win128));
+  memcpy(tw, t.tw, sizeof(t.tw));
+  memcpy(log_frac, t.log_frac, sizeof(int16_t) * 256);
+  memcpy(counter_div, t.counter_div, sizeof(int16_t) * 201);
+  memcpy(log_tab, t.log_tab, sizeof(int16_t) * 9);
+  memcpy(log_idx, t.log_idx, sizeof(int16_t) * 129);
+  memcpy(factor1, t.factor1, sizeof(int16_t) * 257);
+  for (int k = 0; k < 3; ++k) memcpy(factor2 + 257 * k, t.factor2[k], sizeof(int16_t) * 257);
+  memcpy(indicator, t.indicator, sizeof(int16_t) * 17);
+  misc5[0] = t.sum_log_idx5; misc5[1] = t.sum_sq_log_idx5; misc5[2] = t.det5;
+  misc5[3] = t.sum_log_idx65; misc5[4] = t.sum_sq_log_idx65;
+}
