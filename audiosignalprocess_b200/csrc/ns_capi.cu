@@ -390,10 +390,36 @@ int SetPolicy(void* hv, int mode, uint32_t magic) {
 }
 
 // ---- kernel dispatch ---------------------------------------------------------
+// Grid shaping for 148 SMs: a batch of n CTAs runs in ceil(n / (148 R)) rounds when R CTAs are
+// resident per SM.  With R at the register limit the last round is usually part-empty (4096
+// streams: 2048 CTAs / (148*8) = 1.73 rounds); lowering R to the smallest value that keeps the
+// number of rounds makes every round full (R = 7: 2 x 1036 CTAs).  Residency is lowered by
+// padding the dynamic shared memory request.
+constexpr int kNumSms = 148;
+constexpr size_t kSmemPerSm = 227 * 1024;
+size_t BalancedSmem(size_t needed, int n_ctas, int max_resident) {
+  size_t by_smem = kSmemPerSm / (needed + 1024);
+  int rmax = max_resident < (int)by_smem ? max_resident : (int)by_smem;
+  if (rmax < 1) rmax = 1;
+  const int rounds = (n_ctas + kNumSms * rmax - 1) / (kNumSms * rmax);
+  int r = (n_ctas + kNumSms * rounds - 1) / (kNumSms * rounds);
+  if (r >= rmax || r < 1) return needed;
+  size_t padded = kSmemPerSm / (size_t)r - 1024;       // r fit, r + 1 do not
+  padded &= ~(size_t)15;
+  return padded > needed ? padded : needed;
+}
+
 template <int ANA, int NB, bool I16>
 int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
-  const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
+  const size_t need = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
+  const size_t smem = BalancedSmem(need, grid, 8);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kSmemPerSm - 1024));
+    attr_set = true;
+  }
   nsf_process_kernel<ANA, NB, I16><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -410,7 +436,14 @@ int LaunchNsf(int ana, int nb, bool i16, const NsfLaunch& p, cudaStream_t st) {
 template <int ANA, int NB>
 int LaunchNsxT(const NsxLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsxWarpsPerCta - 1) / kNsxWarpsPerCta;
-  const size_t smem = sizeof(uint32_t) * (kNsxCtaTableWords + kNsxWarpsPerCta * kNsxWarpWords);
+  const size_t need = sizeof(uint32_t) * (kNsxCtaTableWords + kNsxWarpsPerCta * kNsxWarpWords);
+  const size_t smem = BalancedSmem(need, grid, 8);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_OK(cudaFuncSetAttribute(nsx_process_kernel<ANA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kSmemPerSm - 1024));
+    attr_set = true;
+  }
   nsx_process_kernel<ANA, NB><<<grid, kNsxWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());

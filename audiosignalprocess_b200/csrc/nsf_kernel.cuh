@@ -32,7 +32,7 @@ namespace nsb200 {
 // 2-warp CTAs, 7 per SM (<= 146 registers): 14 resident streams per SM, so that the
 // headline 4096-stream batch is exactly two balanced rounds over 148 SMs.
 constexpr int kNsfWarpsPerCta = 2;
-constexpr int kNsfCtasPerSm = 7;
+constexpr int kNsfCtasPerSm = 8;
 constexpr int kNsfCtaTableWords = 912;  // win 256 | tw 512 | logi 132 | pad
 constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
 
@@ -359,12 +359,18 @@ nsf_process_kernel(const NsfLaunch p) {
       if (updates < 200) updates++;
       HIw[kH_updates] = updates;
       int cnt[3];
-      bool latch[3];
+      float c1[3], cf[3];
+      // which tracker (if any) is latched into `quantile` this frame: the last one whose
+      // counter expired once updates >= 200, else tracker 2 during start-up (:262-280)
+      int sel = updates < 200 ? 2 : -1;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         cnt[s] = HIr[kH_counter + s];
-        latch[s] = cnt[s] >= 200;
-        HIw[kH_counter + s] = (latch[s] ? 0 : cnt[s]) + 1;
+        const bool latch = cnt[s] >= 200;
+        if (latch && updates >= 200) sel = s;
+        HIw[kH_counter + s] = (latch ? 0 : cnt[s]) + 1;
+        c1[s] = (float)(cnt[s] + 1);
+        cf[s] = (float)cnt[s];
       }
       float noise[G::kSlots];
 #pragma unroll
@@ -379,15 +385,15 @@ nsf_process_kernel(const NsfLaunch p) {
         float quant = r1.z;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const float c1 = (float)(cnt[s] + 1);
           const float delta = dn[s] > 1.f ? fdiv(40.f, dn[s]) : 40.f;
-          if (lmagn[j] > lq[s]) lq[s] += fdiv(0.25f * delta, c1);
-          else lq[s] -= fdiv((1.f - 0.25f) * delta, c1);
+          // one division: QUANTILE*delta/(c+1) upwards, (1-QUANTILE)*delta/(c+1) downwards
+          const bool up = lmagn[j] > lq[s];
+          const float step = fdiv((up ? 0.25f : (1.f - 0.25f)) * delta, c1[s]);
+          lq[s] = up ? lq[s] + step : lq[s] - step;
           if (fabsf(lmagn[j] - lq[s]) < 0.01f)
-            dn[s] = fdiv((float)cnt[s] * dn[s] + 1.f / (2.f * 0.01f), c1);
-          if (latch[s] && updates >= 200) quant = expf(lq[s]);
+            dn[s] = fdiv(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s]);
         }
-        if (updates < 200) quant = expf(lq[2]);
+        if (sel >= 0) quant = expf(sel == 0 ? lq[0] : (sel == 1 ? lq[1] : lq[2]));
         noise[j] = quant;
         if (!nyq || lane == 0) {
           *reinterpret_cast<float4*>(R) = make_float4(lq[0], lq[1], lq[2], dn[0]);
