@@ -49,13 +49,51 @@ inline double band_down_initial_vsi() {
   return vsi;
 }
 
+// Replays SincResampler::Resample's block loop (sinc_resampler.cc:269-342) of a 640 -> 480
+// PushSincResampler for `frames` consecutive calls starting from the running position *vsi
+// (in our coordinates: block of 640, see band_init_vsi), and records for every output where
+// the 32-tap window starts in the kernel's E buffer ([64 history | 640 new]: old block at
+// q - 608, new block at q + 32), the table row and the two interpolation weights exactly as
+// the reference casts them (sinc_resampler_sse.cc:43,45).
+inline void band_down_schedule(double* vsi, int frames, int32_t* sched) {
+  const double r = 640.0 / 480.0;
+  const double block = 640.0;
+  double v = *vsi;
+  for (int f = 0; f < frames; ++f) {
+    int32_t* out = sched + (size_t)f * 480 * 3;
+    int n = 0, remaining = 480;
+    bool shifted = false;
+    while (remaining) {
+      int cnt = (int)ceil((block - v) / r);
+      for (; cnt > 0 && remaining; --cnt) {
+        const int sidx = (int)v;
+        const double voff = (v - sidx) * 32.0;
+        const int off = (int)voff;
+        const double kif = voff - off;
+        const float f2 = (float)kif, f1 = (float)(1.0 - kif);
+        out[3 * n] = ((shifted ? sidx + 32 : sidx - 608) << 8) | off;
+        memcpy(&out[3 * n + 1], &f2, 4);
+        memcpy(&out[3 * n + 2], &f1, 4);
+        v += r;
+        ++n;
+        --remaining;
+      }
+      if (!remaining) break;
+      v -= block;
+      shifted = true;
+    }
+  }
+  *vsi = v;
+}
+
+// After the primed pass the reference still works on its 624-sample first block; we always
+// work on 640-sample blocks whose start lies 16 samples later, so the carried position is
+// shifted by the same 16 samples (exactly representable; the samples in between are the zero
+// priming).
+inline double band_init_vsi() { return band_down_initial_vsi() + 16.0; }
+
 inline void band_init_state(uint32_t* slab) {
   memset(slab, 0, sizeof(uint32_t) * (size_t)kBandStateWords);
-  // After the primed pass the reference still works on its 624-sample first block; our kernel
-  // always works on 640-sample blocks with the block start 16 samples later, so the carried
-  // position is shifted by the same 16 samples (the samples in between are the zero priming).
-  const double v = band_down_initial_vsi() + 16.0;
-  memcpy(slab + kBandOffSynVsi, &v, sizeof(v));
 }
 
 }  // namespace nsb200

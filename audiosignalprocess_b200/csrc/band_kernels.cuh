@@ -22,6 +22,8 @@
 
 #include <stdint.h>
 
+#include <vector>
+
 #include "band_layout.h"
 #include "ns_warp.cuh"
 
@@ -34,8 +36,10 @@ NSB_DEV int band_round_s16(float v) {  // FloatS16ToS16, common_audio/include/au
 }
 // WebRtcSpl_SubSatW32 (spl_inl.h:60)
 NSB_DEV int band_sub_sat(int a, int b) {
-  const long long d = (long long)a - (long long)b;
-  return d > 2147483647LL ? 2147483647 : (d < -2147483648LL ? (int)0x80000000 : (int)d);
+  const int d = (int)((unsigned)a - (unsigned)b);
+  // overflow iff the operands differ in sign and the result's sign differs from a's
+  const bool ovf = ((a ^ b) & (a ^ d)) < 0;
+  return ovf ? (a < 0 ? (int)0x80000000 : 0x7fffffff) : d;
 }
 // WEBRTC_SPL_SCALEDIFF32(A, B, C) = C + (B >> 16) * A + (((uint32_t)(B & 0xFFFF) * A) >> 16)
 NSB_DEV int band_scalediff(unsigned a, int b, int c) {
@@ -199,17 +203,21 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
 
 // ---- sinc resampler -------------------------------------------------------------
 // One warp per stream.  E = [64 history samples | SRC new samples] as floats in
-// shared memory; output n is a 32-tap dot product at virtual position
-// e_n = 32 + vsi_n in E, with kernels k1/k2 = table rows floor/floor+1 of the
-// sub-sample offset * 32 and linear interpolation between them.
-//   UP   (480 -> 640, ratio 0.75, exact in binary): e_n = 31.5 + 0.75 n, closed form.
-//   DOWN (640 -> 480, ratio 4/3 as a double): vsi is the reference's running double,
-//        advanced by repeated addition (sinc_resampler.cc:322) and carried in the
-//        state, so that rounding drift is reproduced exactly.
+// shared memory; output n is a 32-tap dot product at position epos in E with
+// kernels k1/k2 = table rows `off`, `off`+1 and linear interpolation between them.
+//   UP   (480 -> 640, ratio 0.75, exact in binary): e_n = 31.5 + 0.75 n, closed form,
+//        interpolation factor 0.
+//   DOWN (640 -> 480, ratio 4/3 as a double): the reference advances a running double by
+//        repeated addition (sinc_resampler.cc:322), so positions drift by rounding and depend
+//        on the stream's age.  The host owns that double per handle, replays the reference's
+//        block loop for the frames of this launch (band_host_init.h) and passes the resulting
+//        schedule: per output (epos << 8 | off), (float)factor, (float)(1 - factor).
 struct ResampleLaunch {
   int32_t* state;
   const int* slots;
   const float* kernel;        // 33 x 32 taps for this ratio
+  const int32_t* schedule;    // DOWN only: [frames][480][3] words
+  const int* stream_index;    // optional: launch-local index -> batch index (NULL = identity)
   const int16_t* in;
   int16_t* out;
   long long in_stream_stride, in_frame_stride, out_stream_stride, out_frame_stride;
@@ -220,8 +228,7 @@ constexpr int kResampleWarpsPerCta = 4;
 constexpr int kResampleKernelWords = 33 * 33 + 3;        // padded rows, 16-byte multiple
 constexpr int kResampleEWords = 64 + 640 + 32;
 constexpr size_t kResampleSmemBytes =
-    sizeof(float) * (kResampleKernelWords + kResampleWarpsPerCta * kResampleEWords) +
-    sizeof(int) * kResampleWarpsPerCta * 3 * 480;
+    sizeof(float) * (kResampleKernelWords + kResampleWarpsPerCta * kResampleEWords);
 
 template <bool UP>
 __global__ void __launch_bounds__(kResampleWarpsPerCta * 32)
@@ -236,16 +243,14 @@ resample_kernel(const ResampleLaunch p) {
   for (int i = (int)threadIdx.x; i < 33 * 32; i += kResampleWarpsPerCta * 32)
     s_kernel[(i >> 5) * 33 + (i & 31)] = p.kernel[i];
   __syncthreads();
-  const int sidx = (int)blockIdx.x * kResampleWarpsPerCta + warp;
-  if (sidx >= p.n_streams) return;
+  const int lidx = (int)blockIdx.x * kResampleWarpsPerCta + warp;
+  if (lidx >= p.n_streams) return;
+  const int sidx = p.stream_index ? p.stream_index[lidx] : lidx;
   float* E = smem + kResampleKernelWords + warp * kResampleEWords;
-  int* s_pos = reinterpret_cast<int*>(smem + kResampleKernelWords + kResampleWarpsPerCta * kResampleEWords) + warp * 3 * 480;
 
   int32_t* gst = p.state + (size_t)p.slots[sidx] * kBandStateWords;
   int16_t* ghist = reinterpret_cast<int16_t*>(gst + (UP ? kBandOffAnaHist : kBandOffSynHist));
   for (int i = lane; i < 64; i += 32) E[i] = (float)ghist[i];
-  double vsi = 0.0;
-  if (!UP) vsi = *reinterpret_cast<const double*>(gst + kBandOffSynVsi);
   __syncwarp();
 
   for (int f = 0; f < p.frames; ++f) {
@@ -256,37 +261,8 @@ resample_kernel(const ResampleLaunch p) {
       E[64 + 2 * w] = (float)(int16_t)(v & 0xffffu);
       E[64 + 2 * w + 1] = (float)(int16_t)(v >> 16);
     }
-    if (!UP) {
-      // the reference's block loop (sinc_resampler.cc:269-342), positions only; every lane runs
-      // the same serial chain of double additions and lane 0 records it
-      const double r = 640.0 / 480.0;   // io_sample_rate_ratio_, push_sinc_resampler.cc:22
-      const double block = 640.0;
-      int n = 0, remaining = DST;
-      bool shifted = false;
-      while (remaining) {
-        int cnt = (int)ceil((block - vsi) / r);
-        for (; cnt > 0 && remaining; --cnt) {
-          const int sidx_i = (int)vsi;
-          const double rem = vsi - sidx_i;
-          const double voff = rem * 32.0;
-          const int off = (int)voff;
-          const double kif = voff - off;   // kernel_interpolation_factor
-          // position in E: old block at q - 608, new block at q + 32
-          if (lane == 0) {
-            s_pos[3 * n] = ((shifted ? sidx_i + 32 : sidx_i - 608) << 8) | off;
-            reinterpret_cast<float*>(s_pos)[3 * n + 1] = (float)kif;          // sinc_resampler_sse.cc:45
-            reinterpret_cast<float*>(s_pos)[3 * n + 2] = (float)(1.0 - kif);  // :43
-          }
-          vsi += r;
-          ++n;
-          --remaining;
-        }
-        if (!remaining) break;
-        vsi -= block;
-        shifted = true;
-      }
-    }
     __syncwarp();
+    const int32_t* sch = UP ? nullptr : p.schedule + (size_t)f * 480 * 3;
 #pragma unroll 1
     for (int t = 0; t < NOUT; ++t) {
       const int n = lane + 32 * t;
@@ -301,11 +277,11 @@ resample_kernel(const ResampleLaunch p) {
         fac = 0.f;
         fac1 = 1.f;
       } else {
-        const int pk = s_pos[3 * n];
+        const int pk = sch[3 * n];
         epos = pk >> 8;
         off = pk & 0xff;
-        fac = reinterpret_cast<const float*>(s_pos)[3 * n + 1];
-        fac1 = reinterpret_cast<const float*>(s_pos)[3 * n + 2];
+        fac = __int_as_float(sch[3 * n + 1]);
+        fac1 = __int_as_float(sch[3 * n + 2]);
       }
       const float* k1 = s_kernel + off * 33;
       const float* k2 = k1 + 33;
@@ -337,7 +313,6 @@ resample_kernel(const ResampleLaunch p) {
     __syncwarp();
   }
   for (int i = lane; i < 64; i += 32) ghist[i] = (int16_t)E[i];
-  if (!UP && lane == 0) *reinterpret_cast<double*>(gst + kBandOffSynVsi) = vsi;
 }
 
 // ---- launch helpers (host) -------------------------------------------------------
@@ -346,6 +321,10 @@ struct BandLaunch {
   const int* slots;
   const float* kernel_up;     // resampler tables (device)
   const float* kernel_down;
+  // 48 kHz merge: the 640 -> 480 resampler runs once per group of streams that share a
+  // position schedule (normally one group = the whole batch)
+  struct DownGroup { const int32_t* schedule; const int* stream_index; int count; };
+  std::vector<DownGroup> down_groups;
   int16_t* full;              // full-band PCM [stream][frame][fs/100]
   long long full_stride;
   int16_t* bands;             // [stream][frame][nb][160]
@@ -448,13 +427,16 @@ inline int LaunchBandMerge(int nb, const BandLaunch& b, cudaStream_t st, uint64_
   q.out[0] = s64; q.out_stream_stride[0] = ss; q.out_frame_stride[0] = 640;
   qmf_synthesis_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(q);
   ++*launches;
-  ResampleLaunch r = {};
-  r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_down; r.in = s64; r.out = b.full;
-  r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_stride; r.out_frame_stride = 480;
-  r.n_streams = n; r.frames = F;
-  const size_t smem = kResampleSmemBytes;
-  resample_kernel<false><<<(n + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta, kResampleWarpsPerCta * 32, smem, st>>>(r);
-  ++*launches;
+  for (const BandLaunch::DownGroup& g : b.down_groups) {
+    ResampleLaunch r = {};
+    r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_down; r.schedule = g.schedule;
+    r.stream_index = g.stream_index; r.in = s64; r.out = b.full;
+    r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_stride; r.out_frame_stride = 480;
+    r.n_streams = g.count; r.frames = F;
+    resample_kernel<false><<<(g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta,
+                             kResampleWarpsPerCta * 32, kResampleSmemBytes, st>>>(r);
+    ++*launches;
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -14,7 +14,6 @@ enum : int {
   kBandOffQmf2 = 48,   // band2_states_: 16-32 kHz half -> (dropped), band 2
   kBandOffAnaHist = 72,    // 64 int16: last input samples of the 480 -> 640 resampler
   kBandOffSynHist = 104,   // 64 int16: last input samples of the 640 -> 480 resampler
-  kBandOffSynVsi = 136,    // double: SincResampler::virtual_source_idx_ of the 640 -> 480 resampler
   kBandStateWords = 160,
 };
 

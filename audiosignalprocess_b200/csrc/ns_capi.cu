@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -54,6 +55,7 @@ struct Handle {
   int init_flag;
   bool analyze_seen;
   float analyze_frame[160];
+  double down_vsi;   // 48 kHz: running position of the 640 -> 480 resampler (band_host_init.h)
 };
 
 // Growable pool of fixed-size slabs in device memory.
@@ -88,6 +90,8 @@ struct DeviceCtx {
   size_t bands_elems = 0;
   int16_t* d_band_scratch = nullptr;   // 48 kHz: 64 kHz and 32 kHz intermediates
   size_t band_scratch_elems = 0;
+  int32_t* d_down_sched = nullptr;     // 48 kHz: resampler schedule of the current launch
+  size_t down_sched_words = 0;
 };
 
 std::vector<DeviceCtx> g_devs;
@@ -347,6 +351,7 @@ int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
     h->mode = mode;
     h->init_flag = 1;
     h->analyze_seen = false;
+    h->down_vsi = band_init_vsi();
   }
   return 0;
 }
@@ -390,36 +395,15 @@ int SetPolicy(void* hv, int mode, uint32_t magic) {
 }
 
 // ---- kernel dispatch ---------------------------------------------------------
-// Grid shaping for 148 SMs: a batch of n CTAs runs in ceil(n / (148 R)) rounds when R CTAs are
-// resident per SM.  With R at the register limit the last round is usually part-empty (4096
-// streams: 2048 CTAs / (148*8) = 1.73 rounds); lowering R to the smallest value that keeps the
-// number of rounds makes every round full (R = 7: 2 x 1036 CTAs).  Residency is lowered by
-// padding the dynamic shared memory request.
-constexpr int kNumSms = 148;
-constexpr size_t kSmemPerSm = 227 * 1024;
-size_t BalancedSmem(size_t needed, int n_ctas, int max_resident) {
-  size_t by_smem = kSmemPerSm / (needed + 1024);
-  int rmax = max_resident < (int)by_smem ? max_resident : (int)by_smem;
-  if (rmax < 1) rmax = 1;
-  const int rounds = (n_ctas + kNumSms * rmax - 1) / (kNumSms * rmax);
-  int r = (n_ctas + kNumSms * rounds - 1) / (kNumSms * rounds);
-  if (r >= rmax || r < 1) return needed;
-  size_t padded = kSmemPerSm / (size_t)r - 1024;       // r fit, r + 1 do not
-  padded &= ~(size_t)15;
-  return padded > needed ? padded : needed;
-}
-
+// Residency: measured on the B200 (tools/bench_variants.sh, profiles/r1_tuning.md) the float
+// kernel is fastest at 8 two-warp CTAs per SM (128 registers, no spills that matter) and the
+// fixed-point kernel at 14 (72 registers); padding shared memory to force "balanced" full waves
+// (7 CTAs/SM = exactly two rounds for 4096 streams) was slower than the fuller occupancy.
 template <int ANA, int NB, bool I16>
 int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
   const size_t need = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
-  const size_t smem = BalancedSmem(need, grid, 8);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)kSmemPerSm - 1024));
-    attr_set = true;
-  }
+  const size_t smem = need;
   nsf_process_kernel<ANA, NB, I16><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -437,13 +421,7 @@ template <int ANA, int NB>
 int LaunchNsxT(const NsxLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsxWarpsPerCta - 1) / kNsxWarpsPerCta;
   const size_t need = sizeof(uint32_t) * (kNsxCtaTableWords + kNsxWarpsPerCta * kNsxWarpWords);
-  const size_t smem = BalancedSmem(need, grid, 8);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_OK(cudaFuncSetAttribute(nsx_process_kernel<ANA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)kSmemPerSm - 1024));
-    attr_set = true;
-  }
+  const size_t smem = need;
   nsx_process_kernel<ANA, NB><<<grid, kNsxWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -461,7 +439,7 @@ int NumBands(uint32_t fs) { return fs == 32000 ? 2 : (fs == 48000 ? 3 : 1); }
 
 // Enqueues split -> NS -> merge for `idx.size()` streams of one device whose
 // full-band int16 PCM sits in device memory.
-int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, const int16_t* d_in,
+int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in,
               size_t in_stride, int16_t* d_out, size_t out_stride, int frames, cudaStream_t st) {
   const int n = (int)hs.size();
   const uint32_t fs = hs[0]->fs;
@@ -564,6 +542,62 @@ int RunDevice(DeviceCtx& d, uint32_t magic, const std::vector<Handle*>& hs, cons
     b.kernel_up = d.d_sinc_up;
     b.kernel_down = d.d_sinc_down;
     b.scratch = d.d_band_scratch;
+    if (nb == 3) {
+      // 640 -> 480 resampler positions: replay the reference's running double per distinct
+      // starting value, group streams whose schedules coincide (streams of different age differ
+      // by ~1e-13 in position, which almost never changes a table row or a float weight)
+      const size_t words = (size_t)frames * 480 * 3;
+      std::vector<std::vector<int32_t>> scheds;
+      std::vector<std::vector<int>> members;
+      std::vector<std::pair<double, std::pair<int, double>>> seen;   // start -> (group, end)
+      for (int i = 0; i < n; ++i) {
+        const double v0 = hs[i]->down_vsi;
+        int gi = -1;
+        double vend = 0;
+        for (auto& s : seen)
+          if (memcmp(&s.first, &v0, sizeof(double)) == 0) { gi = s.second.first; vend = s.second.second; break; }
+        if (gi < 0) {
+          std::vector<int32_t> sc(words);
+          double v = v0;
+          band_down_schedule(&v, frames, sc.data());
+          vend = v;
+          for (size_t g = 0; g < scheds.size(); ++g)
+            if (memcmp(scheds[g].data(), sc.data(), words * sizeof(int32_t)) == 0) { gi = (int)g; break; }
+          if (gi < 0) {
+            gi = (int)scheds.size();
+            scheds.push_back(std::move(sc));
+            members.emplace_back();
+          }
+          seen.push_back({v0, {gi, vend}});
+        }
+        members[gi].push_back(i);
+        hs[i]->down_vsi = vend;
+      }
+      const size_t need_w = scheds.size() * words + (scheds.size() > 1 ? (size_t)n : 0);
+      if (need_w > d.down_sched_words) {
+        CU_OK(cudaStreamSynchronize(st));
+        if (d.d_down_sched) CU_OK(cudaFree(d.d_down_sched));
+        CU_OK(cudaMalloc(&d.d_down_sched, sizeof(int32_t) * need_w));
+        d.down_sched_words = need_w;
+      }
+      int32_t* d_idx = d.d_down_sched + scheds.size() * words;
+      size_t idx_off = 0;
+      for (size_t g = 0; g < scheds.size(); ++g) {
+        CU_OK(cudaMemcpyAsync(d.d_down_sched + g * words, scheds[g].data(), sizeof(int32_t) * words,
+                              cudaMemcpyHostToDevice, st));
+        BandLaunch::DownGroup dg;
+        dg.schedule = d.d_down_sched + g * words;
+        dg.count = (int)members[g].size();
+        dg.stream_index = nullptr;
+        if (scheds.size() > 1) {
+          CU_OK(cudaMemcpyAsync(d_idx + idx_off, members[g].data(), sizeof(int) * members[g].size(),
+                                cudaMemcpyHostToDevice, st));
+          dg.stream_index = reinterpret_cast<const int*>(d_idx + idx_off);
+          idx_off += members[g].size();
+        }
+        b.down_groups.push_back(dg);
+      }
+    }
     if (LaunchBandMerge(nb, b, st, &g_launches) != 0) return Fail("band merge launch failed");
   }
   return 0;

@@ -32,7 +32,10 @@ namespace nsb200 {
 // 2-warp CTAs, 7 per SM (<= 146 registers): 14 resident streams per SM, so that the
 // headline 4096-stream batch is exactly two balanced rounds over 148 SMs.
 constexpr int kNsfWarpsPerCta = 2;
-constexpr int kNsfCtasPerSm = 8;
+#ifndef NSF_CTAS_PER_SM
+#define NSF_CTAS_PER_SM 8
+#endif
+constexpr int kNsfCtasPerSm = NSF_CTAS_PER_SM;
 constexpr int kNsfCtaTableWords = 912;  // win 256 | tw 512 | logi 132 | pad
 constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
 

@@ -27,7 +27,10 @@
 namespace nsb200 {
 
 constexpr int kNsxWarpsPerCta = 2;
-constexpr int kNsxCtasPerSm = 8;
+#ifndef NSX_CTAS_PER_SM
+#define NSX_CTAS_PER_SM 14
+#endif
+constexpr int kNsxCtasPerSm = NSX_CTAS_PER_SM;
 constexpr int kNsxCtaTableWords = 128 + 128 + 128;   // window | twiddles | log2 fraction table
 constexpr int kNsxScratchWords = 256 + 136;          // FFT transposes | time / spectrum buffer
 constexpr int kNsxWarpWords = 2 * kNsxHdrWords + 2 * 129 * 4 + kNsxScratchWords;

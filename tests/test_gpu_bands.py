@@ -43,3 +43,39 @@ def test_float_multiband_parity(nslib, reflib, fs, mode):
         res.append(judge_float(refi, out[s], slack=1.0))
     summarize_parity(res, "float multi-band fs=%d mode=%d" % (fs, mode), 0.6)
     b.close()
+
+
+def test_48k_streams_of_different_age_in_one_batch(nslib, reflib):
+    """Streams that joined at different times share a launch: the 640 -> 480 resampler's position
+    (a running double in the reference) is tracked per handle, so every stream still matches."""
+    import ctypes as C
+    fs, mode, fl = 48000, 2, 480
+    lib = nslib.load_library()
+    n, head, total = 4, 37, 120
+    x = nslib.synth_pcm_host(n, fs, total * fl)
+    hs = (C.c_void_p * n)()
+    for i in range(n):
+        h = C.c_void_p()
+        assert lib.WebRtcNsx_Create(C.byref(h)) == 0
+        hs[i] = h
+    assert lib.WebRtcNsx_InitBatch(hs, n, fs, mode) == 0
+    out = np.zeros_like(x)
+    # streams 0,1 run alone for `head` frames ...
+    a = np.ascontiguousarray(x[:2, :head * fl])
+    oa = np.zeros_like(a)
+    assert lib.WebRtcNsx_ProcessBatch(hs, 2, a.ctypes.data_as(C.c_void_p), a.shape[1],
+                                      oa.ctypes.data_as(C.c_void_p), oa.shape[1], head) == 0
+    out[:2, :head * fl] = oa
+    # ... then all four share launches: 0,1 continue, 2,3 start from their own sample 0
+    rest = total - head
+    b = np.ascontiguousarray(np.concatenate([x[:2, head * fl:], x[2:, :rest * fl]], axis=0))
+    ob = np.zeros_like(b)
+    assert lib.WebRtcNsx_ProcessBatch(hs, n, b.ctypes.data_as(C.c_void_p), b.shape[1],
+                                      ob.ctypes.data_as(C.c_void_p), ob.shape[1], rest) == 0
+    out[:2, head * fl:] = ob[:2]
+    for s in range(2):
+        assert np.array_equal(out[s], reflib.nsx(fs, mode, x[s]))
+    for s in range(2, 4):
+        assert np.array_equal(ob[s], reflib.nsx(fs, mode, x[s][:rest * fl]))
+    for i in range(n):
+        lib.WebRtcNsx_Free(hs[i])
