@@ -36,6 +36,20 @@ def algorithmic_bytes(kind, fs, frames_per_launch):
     return io + 2.0 * S_HOT[(kind, fs)] / frames_per_launch
 
 
+def measured_traffic(kernel, frames_per_launch, streams):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary of the SAME
+    configuration (profiles/r1_*.json), else None."""
+    tag = {"nsf_process_kernel": "nsf", "nsx_process_kernel": "nsx"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", "r1_%s_kernel_F%d.json" % (tag, frames_per_launch))
+    try:
+        d = json.load(open(path))
+        if d["units_per_launch"] == streams * frames_per_launch:
+            return d["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -249,8 +263,10 @@ def main():
         med = sorted(step_ms)[len(step_ms) // 2]
         avg_ms = ms_total / a.steps      # rank 0's own launches
         achieved = bytes_per_sf * a.streams * F / (avg_ms * 1e-3) / 1e9
+        kname = "nsx_process_kernel" if a.fixed else "nsf_process_kernel"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": which, "kernel": "nsx_process_kernel" if a.fixed else "nsf_process_kernel",
+                    "traffic": measured_traffic(kname, F, a.streams) if a.fs == 16000 else None,
+                    "peak_source": which, "kernel": kname,
                     "bytes_per_stream_frame": bytes_per_sf, "frames_per_launch": F,
                     "launch_ms_avg": avg_ms, "launch_ms_median": med}
         cpu = None
