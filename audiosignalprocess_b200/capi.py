@@ -27,6 +27,8 @@ SYMBOLS = {
     "WebRtcNs_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNsx_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNs_ProcessBatchBandsF32": (C.c_int, [_HP, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "WebRtcNs_ProcessInterleavedI16": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_int]),
+    "WebRtcNs_ProcessInterleavedF32": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_int]),
     "WebRtcNs_InitBatch": (C.c_int, [_HP, C.c_int, C.c_uint32, C.c_int]),
     "WebRtcNsx_InitBatch": (C.c_int, [_HP, C.c_int, C.c_uint32, C.c_int]),
     "WebRtcNsB200_SetCreateDevice": (C.c_int, [C.c_int]),

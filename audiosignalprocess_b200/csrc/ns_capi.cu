@@ -775,6 +775,41 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
   return rc;
 }
 
+// ---- interleaved multi-channel front end (APM_NS::processCaptureStream, libapm/src/apm_ns.cpp:47-132)
+// FloatToS16 / S16ToFloat of common_audio/include/audio_util.h:27-39.
+__device__ __forceinline__ int float_to_s16(float v) {
+  if (v > 0.f) return v >= 1.f ? 32767 : (int)(int16_t)(v * 32767.f + 0.5f);
+  return v <= -1.f ? -32768 : (int)(int16_t)(-v * -32768.f - 0.5f);
+}
+__device__ __forceinline__ float s16_to_float(int v) {
+  const float kMaxInv = 1.f / 32767.f, kMinInv = 1.f / -32768.f;
+  return (float)v * (v > 0 ? kMaxInv : -kMinInv);
+}
+// interleaved [sample][channel] -> planar [channel][samples] int16
+template <typename T>
+__global__ void deinterleave_kernel(const T* in, int16_t* out, int channels, int samples) {
+  const size_t total = (size_t)channels * samples;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % channels);
+    const size_t n = i / channels;
+    int v;
+    if (sizeof(T) == 2) v = (int)reinterpret_cast<const int16_t*>(in)[i];
+    else v = float_to_s16(reinterpret_cast<const float*>(in)[i]);
+    out[(size_t)c * samples + n] = (int16_t)v;
+  }
+}
+template <typename T>
+__global__ void interleave_kernel(const int16_t* in, T* out, int channels, int samples) {
+  const size_t total = (size_t)channels * samples;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % channels);
+    const size_t n = i / channels;
+    const int v = in[(size_t)c * samples + n];
+    if (sizeof(T) == 2) reinterpret_cast<int16_t*>(out)[i] = (int16_t)v;
+    else reinterpret_cast<float*>(out)[i] = s16_to_float(v);
+  }
+}
+
 // Device self-test of the arithmetic shortcuts: fdiv() against IEEE division and
 // fx_sqrt_floor() against the reference's restoring iteration (spl_sqrt_floor.c:55),
 // over pseudo-random operands in the kernels' ranges.  Counts mismatches.
@@ -799,6 +834,9 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
   }
   if (mism) atomicAdd(bad, mism);
 }
+
+template <typename T>
+int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_channel);
 
 __global__ void synth_kernel(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream,
                              uint32_t fs, uint32_t first_sample, uint32_t n_samples, uint32_t seed) {
@@ -839,6 +877,47 @@ __global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams
     sums[2 * s] = sa[0];
     sums[2 * s + 1] = sb[0];
   }
+}
+
+// One device: H2D interleaved -> deinterleave (+FloatToS16) -> split/NS/merge -> interleave
+// (+S16ToFloat) -> D2H, in place (apm_ns.cpp:47-132 does the same per 10 ms on the host).
+template <typename T>
+int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_channel) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!data) return Fail("NULL data");
+  std::vector<Handle*> hs;
+  if (CheckBatch(hv, channels, kMagicF, 0, 0, 0, &hs) != 0) return -1;
+  const int fl = (int)hs[0]->fs / 100;
+  if (samples_per_channel <= 0 || samples_per_channel % fl) return Fail("samples_per_channel must be a multiple of fs/100");
+  for (int i = 1; i < channels; ++i)
+    if (hs[i]->dev != hs[0]->dev) return Fail("channels of one capture stream must share a GPU");
+  DeviceCtx* d;
+  if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
+  const int frames = samples_per_channel / fl;
+  const size_t total = (size_t)channels * samples_per_channel;
+  const size_t per = (size_t)samples_per_channel;   // fs/100 is a multiple of 8: rows stay 16-byte aligned
+  T* d_il = nullptr;
+  int16_t* d_pl = nullptr;
+  CU_OK(cudaMalloc(&d_il, sizeof(T) * total));
+  CU_OK(cudaMalloc(&d_pl, sizeof(int16_t) * per * channels));
+  int rc = 0;
+  do {
+    cudaError_t e = cudaMemcpyAsync(d_il, data, sizeof(T) * total, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    deinterleave_kernel<T><<<grid, 256, 0, d->stream>>>(d_il, d_pl, channels, samples_per_channel);
+    ++g_launches;
+    if ((rc = RunDevice(*d, kMagicF, hs, d_pl, per, d_pl, per, frames, d->stream)) != 0) break;
+    interleave_kernel<T><<<grid, 256, 0, d->stream>>>(d_pl, d_il, channels, samples_per_channel);
+    ++g_launches;
+    e = cudaMemcpyAsync(data, d_il, sizeof(T) * total, cudaMemcpyDeviceToHost, d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+  } while (0);
+  cudaFree(d_il);
+  cudaFree(d_pl);
+  return rc;
 }
 
 }  // namespace
@@ -968,6 +1047,12 @@ int WebRtcNsx_ProcessBatchDevice(NsxHandle* const* hs, int n, const int16_t* in,
 int WebRtcNs_ProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* in, size_t is, float* out,
                                   size_t os, int frames) {
   return ProcessBandsF32(reinterpret_cast<void* const*>(hs), n, nb, in, is, out, os, frames);
+}
+int WebRtcNs_ProcessInterleavedI16(NsHandle* const* hs, int n_channels, int16_t* data, int samples_per_channel) {
+  return ProcessInterleaved<int16_t>(reinterpret_cast<void* const*>(hs), n_channels, data, samples_per_channel);
+}
+int WebRtcNs_ProcessInterleavedF32(NsHandle* const* hs, int n_channels, float* data, int samples_per_channel) {
+  return ProcessInterleaved<float>(reinterpret_cast<void* const*>(hs), n_channels, data, samples_per_channel);
 }
 int WebRtcNs_InitBatch(NsHandle* const* hs, int n, uint32_t fs, int mode) {
   return InitMany(reinterpret_cast<void* const*>(hs), n, fs, mode, kMagicF);

@@ -98,6 +98,17 @@ int WebRtcNsx_ProcessBatchDevice(NsxHandle* const* handles, int n_streams, const
 int WebRtcNs_ProcessBatchBandsF32(NsHandle* const* handles, int n_streams, int num_bands,
                                   const float* in, size_t in_stream_stride, float* out,
                                   size_t out_stream_stride, int frames);
+/*
+ * Interleaved multi-channel capture block, processed in place: the job of the author's wrapper
+ * APM_NS::processCaptureStream (libapm/src/apm_ns.cpp:91-132 short, :47-89 float) -- deinterleave
+ * (float samples in [-1, 1] through FloatToS16, audio_util.h:27-32), band split, Analyze + Process
+ * per channel (handles[c] = channel c), merge, interleave (S16ToFloat) -- with the (de)interleave
+ * and conversions done on the GPU.  samples_per_channel = frames * fs/100, a multiple of 8.
+ */
+int WebRtcNs_ProcessInterleavedI16(NsHandle* const* handles, int n_channels, int16_t* data,
+                                   int samples_per_channel);
+int WebRtcNs_ProcessInterleavedF32(NsHandle* const* handles, int n_channels, float* data,
+                                   int samples_per_channel);
 /* Init + set_policy for many handles with one launch (same effect as calling
  * WebRtcNs_Init / WebRtcNs_set_policy on each). */
 int WebRtcNs_InitBatch(NsHandle* const* handles, int n_streams, uint32_t fs, int mode);

@@ -25,6 +25,7 @@
 #include "webrtc/common_audio/resampler/push_sinc_resampler.h"
 #include "webrtc/common_audio/signal_processing/include/real_fft.h"
 #include "webrtc/common_audio/signal_processing/include/signal_processing_library.h"
+#include "libapm/include/apm_ns.h"
 #include "webrtc/modules/audio_processing/audio_buffer.h"
 #include "webrtc/modules/audio_processing/ns/include/noise_suppression.h"
 #include "webrtc/modules/audio_processing/ns/include/noise_suppression_x.h"
@@ -201,6 +202,23 @@ void ref_split_synthesis(void* p, const int16_t* bands, int n, int16_t* out) {
     memcpy(ab->split_bands(0)[b], bands + 160 * b, sizeof(int16_t) * 160);
   ab->MergeFrequencyBands();
   memcpy(out, ab->data_const(0), sizeof(int16_t) * n);
+}
+
+// The author's wrapper class (libapm/src/apm_ns.cpp), one AudioBuffer frame per call.
+void* ref_apm_ns_create(unsigned fs, int mode, int frame, int channels) {
+  APM_NS* a = new APM_NS();
+  if (!a->initNsModule(fs, mode, frame, channels)) {
+    delete a;
+    return NULL;
+  }
+  return a;
+}
+void ref_apm_ns_free(void* a) { delete (APM_NS*)a; }
+void ref_apm_ns_process_i16(void* a, int16_t* data, int frame, int channels) {
+  ((APM_NS*)a)->processCaptureStream(data, frame, channels);
+}
+void ref_apm_ns_process_f32(void* a, float* data, int frame, int channels) {
+  ((APM_NS*)a)->processCaptureStream(data, frame, channels);
 }
 
 // SPL scalar helpers (signal_processing_unittest.cc KAT values).
