@@ -30,7 +30,7 @@ def _ref_run(reflib, fs, mode, x_il, channels, as_float):
     return out
 
 
-@pytest.mark.parametrize("fs,channels,as_float", [(16000, 2, False), (48000, 2, False), (16000, 3, True), (32000, 2, True)])
+@pytest.mark.parametrize("fs,channels,as_float", [(16000, 2, False), (48000, 2, False), (16000, 1, True), (32000, 2, True)])  # the reference AudioBuffer asserts <= 2 channels
 def test_interleaved_matches_apm_ns(nslib, reflib, fs, channels, as_float):
     mode, frames, fl = 2, 400, fs // 100
     lib = nslib.load_library()
