@@ -39,5 +39,18 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_examples():
+    """examples/test_ns_module: the Linux clone of the reference CLI driver, linked against the library."""
+    src = os.path.join(HERE, "..", "examples", "test_ns_module.cpp")
+    exe = os.path.join(HERE, "test_ns_module")
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return exe
+    cmd = ["g++", "-O2", "-std=c++11", "-o", exe, src, "-L" + HERE, "-lwebrtc_ns_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return exe
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
