@@ -203,10 +203,12 @@ nsf_process_kernel(const NsfLaunch p) {
   // ---- state: HBM -> shared / registers
   Hr[lane] = gS[lane];
   {
+    // per-bin records: asynchronous copy, awaited just before the first use (noise estimation)
     const float4* src = reinterpret_cast<const float4*>(gS + kNsfOffBins);
     float4* dst = reinterpret_cast<float4*>(B);
-    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) dst[i] = src[i];
+    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) async_copy16(dst + i, src + i);
   }
+  bool state_ready = false;
   float2 hx[2], sy[2];       // analysis history / synthesis overlap, pair p = lane + 32u
   float2 hb[NB > 1 ? NB - 1 : 1][2];
 #pragma unroll
@@ -357,6 +359,11 @@ nsf_process_kernel(const NsfLaunch p) {
       warp_sum2(sigE, sumMagn);
       const float signalEnergy = sigE / magnLenF;
 
+      if (!state_ready) {
+        async_copy_wait_all();
+        __syncwarp();
+        state_ready = true;
+      }
       // ---- (d) NoiseEstimation (ns_core.c:217-285)
       int updates = HIr[kH_updates];
       if (updates < 200) updates++;
@@ -375,7 +382,7 @@ nsf_process_kernel(const NsfLaunch p) {
         c1[s] = (float)(cnt[s] + 1);
         cf[s] = (float)cnt[s];
       }
-      float noise[G::kSlots];
+      float noise[G::kSlots], smoothPrev[G::kSlots];
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
@@ -386,6 +393,7 @@ nsf_process_kernel(const NsfLaunch p) {
         float lq[3] = {r0.x, r0.y, r0.z};
         float dn[3] = {r0.w, r1.x, r1.y};
         float quant = r1.z;
+        smoothPrev[j] = r1.w;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           const float delta = dn[s] > 1.f ? fdiv(40.f, dn[s]) : 40.f;
@@ -400,9 +408,8 @@ nsf_process_kernel(const NsfLaunch p) {
         noise[j] = quant;
         if (!nyq || lane == 0) {
           *reinterpret_cast<float4*>(R) = make_float4(lq[0], lq[1], lq[2], dn[0]);
-          R[kB_dens1] = dn[1];
-          R[kB_dens2] = dn[2];
-          R[kB_quantile] = quant;
+          // whole 16-byte groups only: scalar accesses at a 12-word lane stride are 4-way bank conflicts
+          *reinterpret_cast<float4*>(R + 4) = make_float4(dn[1], dn[2], quant, r1.w);
         }
       }
 
@@ -478,7 +485,7 @@ nsf_process_kernel(const NsfLaunch p) {
         const bool nyq = (j == G::kSlots - 1);
         const int k = nyq ? G::kNC : lane + 32 * j;
         const float* R = B + k * kNsfBinRec;
-        const float smooth = R[kB_smooth];
+        const float smooth = smoothPrev[j];
         const float4 r2 = *reinterpret_cast<const float4*>(R + 8);  // noisePrev magnPrev logLrt pause
         noisePrev[j] = r2.x;
         logLrt[j] = r2.z;
@@ -813,6 +820,7 @@ nsf_process_kernel(const NsfLaunch p) {
   }
 
   // ---- state: shared / registers -> HBM
+  if (!state_ready) async_copy_wait_all();
   __syncwarp();
   gS[lane] = Hr[lane];
   {
