@@ -224,10 +224,12 @@ nsx_process_kernel(const NsxLaunch p) {
 
   // ---- state: HBM -> shared / registers
   Hr[lane] = (int)gS[lane];
+  // per-bin records: asynchronous copy (cp.async), awaited before the first use
   for (int i = lane; i < NBIN; i += 32) {
-    RA[i] = reinterpret_cast<const uint4*>(gS + kNsxOffRecA)[i];
-    RB[i] = reinterpret_cast<const uint4*>(gS + kNsxOffRecB)[i];
+    async_copy16(&RA[i], reinterpret_cast<const uint4*>(gS + kNsxOffRecA) + i);
+    async_copy16(&RB[i], reinterpret_cast<const uint4*>(gS + kNsxOffRecB) + i);
   }
+  bool state_ready = false;
   int ana_h[3], syn_h[3], hb_h[NB > 1 ? NB - 1 : 1][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -483,6 +485,11 @@ nsx_process_kernel(const NsxLaunch p) {
         Hw[kX_featFlat] = (int)feat_flat;
       }
 
+      if (!state_ready) {
+        async_copy_wait_all();
+        __syncwarp();
+        state_ready = true;
+      }
       // ---- NoiseEstimation (nsx_core.c:334-452)
       unsigned noise[NSLOT];
       int q_noise = Hr[kX_qNoise];
@@ -1187,6 +1194,7 @@ nsx_process_kernel(const NsxLaunch p) {
   }
 
   // ---- state: shared / registers -> HBM
+  if (!state_ready) async_copy_wait_all();
   __syncwarp();
   gS[lane] = (uint32_t)Hr[lane];
   for (int i = lane; i < NBIN; i += 32) {
