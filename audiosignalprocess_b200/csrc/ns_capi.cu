@@ -92,6 +92,7 @@ struct DeviceCtx {
   size_t band_scratch_elems = 0;
   int32_t* d_down_sched = nullptr;     // 48 kHz: resampler schedule of the current launch
   size_t down_sched_words = 0;
+  std::vector<cudaEvent_t> events;     // host-pointer batch pipeline (reused across calls)
 };
 
 std::vector<DeviceCtx> g_devs;
@@ -652,16 +653,45 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     if (!runs.empty() && runs.back().dev == hs[i]->dev) runs.back().count++;
     else runs.push_back(Run{hs[i]->dev, i, 1});
   }
-  // chunking: >= 4 chunks when there is enough work, so that copy-in, kernel and
-  // copy-out of neighbouring chunks overlap (PCIe is full duplex)
+  // chunking: the copies bound the call (PCIe, ~50 GB/s each way, full duplex) as soon as the
+  // kernel keeps up, so the pipeline wants many small chunks -- fill and drain cost one chunk of
+  // copy-in, kernel and copy-out each -- but chunks large enough that DMA set-up, launch overhead
+  // and the kernel's per-launch state round trip stay small: ~12 MB per direction per chunk.
   int chunk = frames;
-  if (frames >= 16) chunk = (frames + 3) / 4;
-  if (chunk > 250) chunk = 250;
+  {
+    const double bytes_per_frame = (double)n * fl * sizeof(int16_t);
+    int c = (int)(12.0e6 / bytes_per_frame + 0.5);
+    if (c < 5) c = 5;
+    if (frames >= 16 && c > (frames + 3) / 4) c = (frames + 3) / 4;
+    if (c > 250) c = 250;
+    if (const char* e = getenv("NSB200_CHUNK_FRAMES")) {
+      const int v = atoi(e);
+      if (v > 0) c = v;
+    }
+    if (c < chunk) chunk = c;
+  }
+  // chunk plan: half-size first and last chunks shorten the pipeline's fill (first copy-in) and
+  // drain (last kernel + last copy-out), which nothing overlaps
+  std::vector<int> starts;   // first frame of each chunk, plus the end
+  {
+    const int edge = chunk >= 4 && frames >= 3 * chunk ? chunk / 2 : chunk;
+    int f0 = 0;
+    starts.push_back(0);
+    f0 += edge < frames ? edge : frames;
+    while (frames - f0 > chunk + edge) { starts.push_back(f0); f0 += chunk; }
+    if (f0 < frames) {
+      starts.push_back(f0);
+      if (frames - f0 > chunk) starts.push_back(frames - edge);
+    }
+    starts.push_back(frames);
+  }
+  const int nchunks = (int)starts.size() - 1;
+  constexpr int kBuf = 3;   // staging buffers per direction
   for (const Run& r : runs) {
     DeviceCtx* d;
     if (DeviceReady(r.dev, &d) != 0) return -1;
     const size_t per = (size_t)chunk * fl;           // samples per stream per chunk
-    const size_t need = 2 * (size_t)r.count * per;   // double buffered
+    const size_t need = kBuf * (size_t)r.count * per;
     if (need > d->stage_elems) {
       CU_OK(cudaDeviceSynchronize());
       if (d->d_in) { CU_OK(cudaFree(d->d_in)); CU_OK(cudaFree(d->d_out)); }
@@ -669,42 +699,69 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
       CU_OK(cudaMalloc(&d->d_out, sizeof(int16_t) * need));
       d->stage_elems = need;
     }
+    const size_t nev = 3 * (size_t)nchunks;
+    while (d->events.size() < nev) {
+      cudaEvent_t e;
+      CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d->events.push_back(e);
+    }
   }
   // One device at a time issues its whole pipeline asynchronously; devices run
   // concurrently because nothing below blocks the host until the final syncs.
-  std::vector<std::vector<cudaEvent_t>> events(runs.size());
   for (size_t ri = 0; ri < runs.size(); ++ri) {
     const Run& r = runs[ri];
     DeviceCtx* d = &g_devs[r.dev];
     CU_OK(cudaSetDevice(r.dev));
     std::vector<Handle*> sub(hs.begin() + r.first, hs.begin() + r.first + r.count);
     const size_t per = (size_t)chunk * fl;
-    const int nchunks = (frames + chunk - 1) / chunk;
-    std::vector<cudaEvent_t>& ev = events[ri];
-    ev.resize(3 * (size_t)nchunks);
-    for (auto& e : ev) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<cudaEvent_t>& ev = d->events;
+    // NSB200_TRACE=1: per-chunk timeline of the three queues on stderr (tuning aid)
+    const bool trace = getenv("NSB200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+      if (!trace) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      tev.push_back(e);
+    };
     for (int c = 0; c < nchunks; ++c) {
-      const int f0 = c * chunk;
-      const int nf = frames - f0 < chunk ? frames - f0 : chunk;
-      int16_t* din = d->d_in + (size_t)(c & 1) * r.count * per;
-      int16_t* dout = d->d_out + (size_t)(c & 1) * r.count * per;
-      // buffer (c&1) was last read by kernel c-2 and last drained by copy-out c-2
-      if (c >= 2) {
-        CU_OK(cudaStreamWaitEvent(d->copy_in, ev[3 * (c - 2) + 1], 0));
-        CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * (c - 2) + 2], 0));
+      const int f0 = starts[c];
+      const int nf = starts[c + 1] - f0;
+      int16_t* din = d->d_in + (size_t)(c % kBuf) * r.count * per;
+      int16_t* dout = d->d_out + (size_t)(c % kBuf) * r.count * per;
+      // buffer c % kBuf was last read by kernel c-kBuf and last drained by copy-out c-kBuf
+      if (c >= kBuf) {
+        CU_OK(cudaStreamWaitEvent(d->copy_in, ev[3 * (c - kBuf) + 1], 0));
+        CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * (c - kBuf) + 2], 0));
       }
+      mark(d->copy_in);
       CU_OK(cudaMemcpy2DAsync(din, per * sizeof(int16_t), in + (size_t)r.first * in_stride + (size_t)f0 * fl,
                               in_stride * sizeof(int16_t), (size_t)nf * fl * sizeof(int16_t), r.count,
                               cudaMemcpyHostToDevice, d->copy_in));
+      mark(d->copy_in);
       CU_OK(cudaEventRecord(ev[3 * c + 0], d->copy_in));
       CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * c + 0], 0));
+      mark(d->stream);
       if (RunDevice(*d, magic, sub, din, per, dout, per, nf, d->stream) != 0) return -1;
+      mark(d->stream);
       CU_OK(cudaEventRecord(ev[3 * c + 1], d->stream));
       CU_OK(cudaStreamWaitEvent(d->copy_out, ev[3 * c + 1], 0));
+      mark(d->copy_out);
       CU_OK(cudaMemcpy2DAsync(out + (size_t)r.first * out_stride + (size_t)f0 * fl,
                               out_stride * sizeof(int16_t), dout, per * sizeof(int16_t),
                               (size_t)nf * fl * sizeof(int16_t), r.count, cudaMemcpyDeviceToHost, d->copy_out));
+      mark(d->copy_out);
       CU_OK(cudaEventRecord(ev[3 * c + 2], d->copy_out));
+    }
+    if (trace) {
+      CU_OK(cudaDeviceSynchronize());
+      for (int c = 0; c < nchunks; ++c) {
+        float t[6];
+        for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
+        fprintf(stderr, "chunk %2d  h2d %.3f-%.3f  kernel %.3f-%.3f  d2h %.3f-%.3f ms\n", c, t[0], t[1], t[2], t[3], t[4], t[5]);
+      }
+      for (auto e : tev) cudaEventDestroy(e);
     }
   }
   for (size_t ri = 0; ri < runs.size(); ++ri) {
@@ -712,7 +769,6 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     CU_OK(cudaSetDevice(runs[ri].dev));
     CU_OK(cudaStreamSynchronize(d->copy_out));
     CU_OK(cudaStreamSynchronize(d->stream));
-    for (auto& e : events[ri]) CU_OK(cudaEventDestroy(e));
   }
   return 0;
 }
@@ -823,6 +879,20 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
     const float a = __uint_as_float((h1 & 0x807fffffu) | (((h1 >> 23) % 60u + 107u) << 23));
     const float b = __uint_as_float((h2 & 0x007fffffu) | (((h2 >> 23) % 60u + 107u) << 23));
     if (__float_as_uint(fdiv(a, b)) != __float_as_uint(__fdiv_rn(a, b))) ++mism;
+    // divisions by compile-time constants with RN(1/b) as the starting reciprocal
+    if (__float_as_uint(NSB_FDIV_C(a, 129.f)) != __float_as_uint(__fdiv_rn(a, 129.f))) ++mism;
+    if (__float_as_uint(NSB_FDIV_C(a, 65.f)) != __float_as_uint(__fdiv_rn(a, 65.f))) ++mism;
+    if (__float_as_uint(NSB_FDIV_C(a, 0.1f)) != __float_as_uint(__fdiv_rn(a, 0.1f))) ++mism;
+    if (__float_as_uint(NSB_FDIV_C(a, 0.05f)) != __float_as_uint(__fdiv_rn(a, 0.05f))) ++mism;
+    {
+      // shared reciprocal: counter + 1 in 1..201 under quantile-tracker numerators
+      const float cb = (float)(h2 % 201u + 1u);
+      if (__float_as_uint(fdiv_r(a, cb, frcp_nr(cb))) != __float_as_uint(__fdiv_rn(a, cb))) ++mism;
+      // round_s16 against the reference's branches
+      const float v = __uint_as_float((h1 & 0x807fffffu) | (((h1 >> 23) % 24u + 120u) << 23));   // |v| in [2^-7, 2^17)
+      const int want = v > 0.f ? (v >= 32766.5f ? 32767 : (int)(v + 0.5f)) : (v <= -32767.5f ? -32768 : (int)(v - 0.5f));
+      if (round_s16(v) != want) ++mism;
+    }
     const float c = (float)(h1 % 401u);   // small integers as in counters
     if (__float_as_uint(fdiv(c, (float)(h2 % 200u + 1u))) != __float_as_uint(__fdiv_rn(c, (float)(h2 % 200u + 1u)))) ++mism;
     int32_t v = (int32_t)h2, root = 0;

@@ -57,8 +57,10 @@ NSB_DEV float sat_s16f(float v) {  // WEBRTC_SPL_SAT(32767, v, -32768)
   return v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v);
 }
 NSB_DEV int round_s16(float v) {  // FloatS16ToS16, common_audio/include/audio_util.h:41-49
-  if (v > 0.f) return v >= 32766.5f ? 32767 : (int)(v + 0.5f);
-  return v <= -32767.5f ? -32768 : (int)(v - 0.5f);
+  // v > 0 ? (v >= 32766.5 ? 32767 : (int)(v + .5)) : (v <= -32767.5 ? -32768 : (int)(v - .5));
+  // v -+ 0.5 is exact below 2^15, so truncating first and clamping after gives the same integers.
+  const int r = (int)(v + copysignf(0.5f, v));
+  return r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
 }
 
 // ---- threshold re-estimation every 500 frames (ns_core.c:337-517), warp parallel.
@@ -230,7 +232,8 @@ nsf_process_kernel(const NsfLaunch p) {
   const float overdrive = Hr[kH_overdrive];
   const float denoiseBound = Hr[kH_denoiseBound];
   const int gainmap = reinterpret_cast<const int*>(Hr)[kH_gainmap];
-  const float magnLenF = (float)G::kBins;
+  constexpr float kMagnLenF = (float)G::kBins;
+  const float magnLenF = kMagnLenF;
 
   // PCM addressing: frame pair w of band b.
   const size_t in_base = (size_t)sidx * (size_t)p.in_stream_stride;
@@ -357,7 +360,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
       __syncwarp();  // scratch is free again
       warp_sum2(sigE, sumMagn);
-      const float signalEnergy = sigE / magnLenF;
+      const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
 
       if (!state_ready) {
         async_copy_wait_all();
@@ -369,7 +372,7 @@ nsf_process_kernel(const NsfLaunch p) {
       if (updates < 200) updates++;
       HIw[kH_updates] = updates;
       int cnt[3];
-      float c1[3], cf[3];
+      float c1[3], cf[3], rc1[3];   // rc1: reciprocal of counter+1, shared by every bin's two divisions
       // which tracker (if any) is latched into `quantile` this frame: the last one whose
       // counter expired once updates >= 200, else tracker 2 during start-up (:262-280)
       int sel = updates < 200 ? 2 : -1;
@@ -380,6 +383,7 @@ nsf_process_kernel(const NsfLaunch p) {
         if (latch && updates >= 200) sel = s;
         HIw[kH_counter + s] = (latch ? 0 : cnt[s]) + 1;
         c1[s] = (float)(cnt[s] + 1);
+        rc1[s] = frcp_nr(c1[s]);
         cf[s] = (float)cnt[s];
       }
       float noise[G::kSlots], smoothPrev[G::kSlots];
@@ -399,10 +403,10 @@ nsf_process_kernel(const NsfLaunch p) {
           const float delta = dn[s] > 1.f ? fdiv(40.f, dn[s]) : 40.f;
           // one division: QUANTILE*delta/(c+1) upwards, (1-QUANTILE)*delta/(c+1) downwards
           const bool up = lmagn[j] > lq[s];
-          const float step = fdiv((up ? 0.25f : (1.f - 0.25f)) * delta, c1[s]);
+          const float step = fdiv_r((up ? 0.25f : (1.f - 0.25f)) * delta, c1[s], rc1[s]);
           lq[s] = up ? lq[s] + step : lq[s] - step;
           if (fabsf(lmagn[j] - lq[s]) < 0.01f)
-            dn[s] = fdiv(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s]);
+            dn[s] = fdiv_r(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s], rc1[s]);
         }
         if (sel >= 0) quant = expf(sel == 0 ? lq[0] : (sel == 1 ? lq[1] : lq[2]));
         noise[j] = quant;
@@ -506,15 +510,15 @@ nsf_process_kernel(const NsfLaunch p) {
       {
         // spectral flatness (:523-556); magn >= 1 so the log(0) exit is dead
         float den = sumMagn - __shfl_sync(kFullMask, magn[0], 0);
-        den = den / magnLenF;
-        const float num = sumLog / magnLenF;
+        den = NSB_FDIV_C(den, kMagnLenF);
+        const float num = NSB_FDIV_C(sumLog, kMagnLenF);
         const float sf = expf(num) / den;
         feat0 = Hr[kH_feat + 0];
         feat0 += 0.3f * (sf - feat0);
         Hw[kH_feat + 0] = feat0;
         // spectral difference (:595-634)
-        const float avgPause = sumPause / magnLenF;
-        const float avgMagn = sumMagn / magnLenF;
+        const float avgPause = NSB_FDIV_C(sumPause, kMagnLenF);
+        const float avgMagn = NSB_FDIV_C(sumMagn, kMagnLenF);
         float cov = 0.f, varP = 0.f, varM = 0.f;
 #pragma unroll
         for (int j = 0; j < G::kSlots; ++j) {
@@ -527,9 +531,9 @@ nsf_process_kernel(const NsfLaunch p) {
           }
         }
         warp_sum3(cov, varP, varM);
-        cov /= magnLenF;
-        varP /= magnLenF;
-        varM /= magnLenF;
+        cov = NSB_FDIV_C(cov, kMagnLenF);
+        varP = NSB_FDIV_C(varP, kMagnLenF);
+        varM = NSB_FDIV_C(varM, kMagnLenF);
         float feat6 = Hr[kH_feat + 6] + signalEnergy;
         float ad = varM - (cov * cov) / (varP + 0.0001f);
         ad = ad / (feat5 + 0.0001f);
@@ -542,9 +546,9 @@ nsf_process_kernel(const NsfLaunch p) {
             // histogram update (:309-334) -- uses the LRT mean of the previous frame
             if (lane == 0) {
               const float f3 = Hr[kH_feat + 3];
-              if (f3 < 1000 * 0.1f && f3 >= 0.f) atomicAdd(gHist + (int)(f3 / 0.1f), 1);
-              if (feat0 < 1000 * 0.05f && feat0 >= 0.f) atomicAdd(gHist + 1000 + (int)(feat0 / 0.05f), 1);
-              if (feat4 < 1000 * 0.1f && feat4 >= 0.f) atomicAdd(gHist + 2000 + (int)(feat4 / 0.1f), 1);
+              if (f3 < 1000 * 0.1f && f3 >= 0.f) atomicAdd(gHist + (int)NSB_FDIV_C(f3, 0.1f), 1);
+              if (feat0 < 1000 * 0.05f && feat0 >= 0.f) atomicAdd(gHist + 1000 + (int)NSB_FDIV_C(feat0, 0.05f), 1);
+              if (feat4 < 1000 * 0.1f && feat4 >= 0.f) atomicAdd(gHist + 2000 + (int)NSB_FDIV_C(feat4, 0.1f), 1);
             }
           }
           if (c3 == 0) {
@@ -581,7 +585,7 @@ nsf_process_kernel(const NsfLaunch p) {
           if (!nyq || lane == 0) lsum += logLrt[j];
         }
         lsum = warp_sum(lsum);
-        const float lrtAvg = lsum / magnLenF;
+        const float lrtAvg = NSB_FDIV_C(lsum, kMagnLenF);
         Hw[kH_feat + 3] = lrtAvg;
         // priorModelPars may have been re-estimated a few lines up (synced): read Hw
         const float thr0 = Hw[kH_priorPars + 0], thr1 = Hw[kH_priorPars + 1], thr2 = Hw[kH_priorPars + 3];
@@ -752,7 +756,7 @@ nsf_process_kernel(const NsfLaunch p) {
           o = scr[pr];
           if (u < 2 && pr < G::kHP) { o.x += sy[u < 2 ? u : 0].x; o.y += sy[u < 2 ? u : 0].y; }
         }
-        o0[u] = make_float2(sat_s16f(o.x), sat_s16f(o.y));
+        o0[u] = I16 ? o : make_float2(sat_s16f(o.x), sat_s16f(o.y));  // round_s16 saturates too
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u)
@@ -801,7 +805,7 @@ nsf_process_kernel(const NsfLaunch p) {
           if (pr < G::kFP) {
             float2 o = scr[pr];
             if (hbApplyGain) { o.x *= hbGain; o.y *= hbGain; }
-            store_pair(f, b + 1, pr, make_float2(sat_s16f(o.x), sat_s16f(o.y)));
+            store_pair(f, b + 1, pr, I16 ? o : make_float2(sat_s16f(o.x), sat_s16f(o.y)));
           }
         }
 #pragma unroll

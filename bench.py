@@ -61,37 +61,66 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed regions (B200_PROFILING.md's clocks line), read
+    in-process through NVML: spawning nvidia-smi ten times a second stalls the CUDA driver calls of
+    the end-to-end pipeline (measured: 5.9 ms instead of 3.6 ms per step).  nvidia-smi is the
+    fallback when NVML cannot be loaded."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []      # (sm_mhz, sm_max_mhz, [reason flags])
         self.stop_flag = False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
-    def run(self):
+    def sample_nvml(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+            nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        self.samples.append((int(sm), int(mx), [bool(r & b) for b in bits]))
+
+    def sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [t.strip() for t in o.strip().split(",")]
+        if len(f) >= 6 and f[0].isdigit() and f[1].isdigit():
+            self.samples.append((int(f[0]), int(f[1]), [t.lower().startswith("active") for t in f[2:6]]))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [t.strip() for t in o.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nv is not None:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nv is not None else 0.5)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": reasons, "samples": len(self.samples), "via": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def ref_lib():
