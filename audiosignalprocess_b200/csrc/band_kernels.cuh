@@ -12,7 +12,7 @@
 // sums, interpolate, (s0+s2)+(s1+s3)) so its int16 output is bit-exact too.
 //
 // Kernels (each walks all F frames of its unit, state in registers):
-//   resample_kernel   warp per stream, lanes over output samples
+//   resample_*_kernel warp per stream, lanes over output samples
 //   qmf_*_kernel      thread per (stream, QMF instance, all-pass chain): the
 //                     cascaded all-pass sections are a non-linear serial
 //                     recurrence over samples (saturating subtract, truncating
@@ -34,29 +34,39 @@ NSB_DEV int band_round_s16(float v) {  // FloatS16ToS16, common_audio/include/au
   if (v > 0.f) return v >= 32766.5f ? 32767 : (int)(v + 0.5f);
   return v <= -32767.5f ? -32768 : (int)(v - 0.5f);
 }
-// WebRtcSpl_SubSatW32 (spl_inl.h:60)
-NSB_DEV int band_sub_sat(int a, int b) {
-  const int d = (int)((unsigned)a - (unsigned)b);
-  // overflow iff the operands differ in sign and the result's sign differs from a's
-  const bool ovf = ((a ^ b) & (a ^ d)) < 0;
-  return ovf ? (a < 0 ? (int)0x80000000 : 0x7fffffff) : d;
-}
 // WEBRTC_SPL_SCALEDIFF32(A, B, C) = C + (B >> 16) * A + (((uint32_t)(B & 0xFFFF) * A) >> 16)
-NSB_DEV int band_scalediff(unsigned a, int b, int c) {
-  return (int)((unsigned)c + (unsigned)(b >> 16) * a + ((((unsigned)b & 0xFFFFu) * a) >> 16));
+// (signal_processing_library.h:87-88).  With B = 65536 hi + lo the two products are hi*A and
+// floor(lo*A / 65536), neither of which overflows for A < 2^16, so their sum is exactly
+// floor(A*B / 65536): one wide multiply and a funnel shift on the recurrence's critical path.
+NSB_DEV int band_scalediff(int a, int b, int c) {
+#ifdef __CUDA_ARCH__
+  long long prod;
+  asm("mul.wide.s32 %0, %1, %2;" : "=l"(prod) : "r"(b), "r"(a));
+#else
+  const long long prod = (long long)b * (long long)a;
+#endif
+  return (int)((unsigned)c + (unsigned)(prod >> 16));
 }
 
 // One sample through the three cascaded first-order all-pass sections of
 // WebRtcSpl_AllPassQMF (splitting_filter_c.c:48-105).  st[0..5] as in the
 // reference: x[-1], y1[-1], y1[-1], y2[-1], y2[-1], y3[-1].
-NSB_DEV int band_allpass3(int x, int (&st)[6], unsigned c0, unsigned c1, unsigned c2) {
-  const int y1 = band_scalediff(c0, band_sub_sat(x, st[1]), st[0]);
+//
+// The reference forms x - y[-1] with WebRtcSpl_SubSatW32 (spl_inl.h:60).  That saturation can
+// never act: a section y[n] = x[n-1] + c (x[n] - y[n-1]) has the impulse response
+// {c, 1-c^2, -c(1-c^2), ...} with absolute sum 1 + 2c, so from zero state |y3| <= 12.05 |x|max
+// through the larger coefficient set (1.651 * 2.497 * 2.923) and 6.99 through the other.  Inputs
+// are int16 sums in Q10, |x| <= 2^26 (synthesis: low +- high), hence every state stays below
+// 8.1e8 and every difference below 1.7e9 < 2^31 (truncation adds < 1 per step).  A plain
+// subtraction is therefore bit-identical and takes four instructions off the serial chain.
+NSB_DEV int band_allpass3(int x, int (&st)[6], int c0, int c1, int c2) {
+  const int y1 = band_scalediff(c0, x - st[1], st[0]);
   st[0] = x;
   st[1] = y1;
-  const int y2 = band_scalediff(c1, band_sub_sat(y1, st[3]), st[2]);
+  const int y2 = band_scalediff(c1, y1 - st[3], st[2]);
   st[2] = y1;
   st[3] = y2;
-  const int y3 = band_scalediff(c2, band_sub_sat(y2, st[5]), st[4]);
+  const int y3 = band_scalediff(c2, y2 - st[5], st[4]);
   st[4] = y2;
   st[5] = y3;
   return y3;
@@ -79,6 +89,8 @@ struct QmfAnaLaunch {
   long long low_stream_stride[2], low_frame_stride[2], high_stream_stride[2], high_frame_stride[2];
 };
 
+constexpr int kQmfDepth = 4;   // prefetch ring depth (groups of 8 samples); divides 20 and 40
+
 __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p) {
   const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   const int chain = t & 1;
@@ -86,8 +98,7 @@ __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p)
   const bool live = unit < p.n_streams * p.instances;
   const int inst = live ? unit % p.instances : 0;
   const int sidx = live ? unit / p.instances : 0;
-  const unsigned c0 = chain == 0 ? 6418u : 21333u, c1 = chain == 0 ? 36982u : 49062u,
-                 c2 = chain == 0 ? 57261u : 63010u;
+  const int c0 = chain == 0 ? 6418 : 21333, c1 = chain == 0 ? 36982 : 49062, c2 = chain == 0 ? 57261 : 63010;
   int st[6] = {0, 0, 0, 0, 0, 0};
   int32_t* gst = nullptr;
   if (live) {
@@ -95,22 +106,40 @@ __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p)
 #pragma unroll
     for (int i = 0; i < 6; ++i) st[i] = gst[i];
   }
-  const int half = p.len / 2;
-  for (int f = 0; f < p.frames; ++f) {
-    const int16_t* in = p.in[inst] + (size_t)sidx * p.in_stream_stride[inst] + (size_t)f * p.in_frame_stride[inst];
-    int16_t* lo = p.low[inst] ? p.low[inst] + (size_t)sidx * p.low_stream_stride[inst] + (size_t)f * p.low_frame_stride[inst] : nullptr;
-    int16_t* hi = p.high[inst] ? p.high[inst] + (size_t)sidx * p.high_stream_stride[inst] + (size_t)f * p.high_frame_stride[inst] : nullptr;
-    for (int i0 = 0; i0 < half; i0 += 8) {
-      // 8 input pairs = 32 bytes, read by both chains of the unit
-      uint32_t w[8];
-      if (live) {
-        const uint4 a = reinterpret_cast<const uint4*>(in + 2 * i0)[0];
-        const uint4 b = reinterpret_cast<const uint4*>(in + 2 * i0)[1];
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-      } else {
+  // Groups of 8 input pairs (32 bytes, read by both chains of the unit) are fetched kQmfDepth
+  // groups ahead into a register ring: the recurrence spends ~200 cycles on a group, a global
+  // load takes several times that.
+  const int gpf = p.len / 16;                 // groups per frame (40 / 20)
+  const int total = p.frames * gpf;           // multiple of kQmfDepth
+  const int16_t* in_base = p.in[inst] + (size_t)sidx * p.in_stream_stride[inst];
+  int16_t* lo_base = p.low[inst] ? p.low[inst] + (size_t)sidx * p.low_stream_stride[inst] : nullptr;
+  int16_t* hi_base = p.high[inst] ? p.high[inst] + (size_t)sidx * p.high_stream_stride[inst] : nullptr;
+  const long long in_fs = p.in_frame_stride[inst];
+  const long long out_fs = chain == 0 ? p.low_frame_stride[inst] : p.high_frame_stride[inst];
+  int16_t* dst_base = chain == 0 ? lo_base : hi_base;
+  uint4 qa[kQmfDepth], qb[kQmfDepth];
+  // fetch / store cursors advance group by group (no division): position in the frame, frame base
+  int fetch_i = 0, store_i = 0;
+  const int16_t* fetch_row = in_base;
+  int16_t* store_row = dst_base;
+  auto fetch = [&](int g, uint4& a, uint4& b) {
+    a = b = make_uint4(0u, 0u, 0u, 0u);
+    if (live && g < total) {
+      const uint4* src = reinterpret_cast<const uint4*>(fetch_row + 16 * fetch_i);
+      a = src[0];
+      b = src[1];
+    }
+    if (++fetch_i == gpf) { fetch_i = 0; fetch_row += in_fs; }
+  };
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = 0u;
-      }
+  for (int d = 0; d < kQmfDepth; ++d) fetch(d, qa[d], qb[d]);
+  for (int g0 = 0; g0 < total; g0 += kQmfDepth) {
+#pragma unroll
+    for (int d = 0; d < kQmfDepth; ++d) {
+      const int g = g0 + d;
+      const uint4 a = qa[d], b = qb[d];
+      fetch(g + kQmfDepth, qa[d], qb[d]);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       uint32_t packed[4];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -124,8 +153,9 @@ __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p)
         if (k & 1) packed[k >> 1] |= (uint32_t)v << 16;
         else packed[k >> 1] = (uint32_t)v & 0xffffu;
       }
-      int16_t* dst = chain == 0 ? lo : hi;
-      if (live && dst) *reinterpret_cast<uint4*>(dst + i0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (live && dst_base)
+        *reinterpret_cast<uint4*>(store_row + 8 * store_i) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (++store_i == gpf) { store_i = 0; store_row += out_fs; }
     }
   }
   if (live) {
@@ -157,8 +187,7 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
   const int inst = live ? unit % p.instances : 0;
   const int sidx = live ? unit / p.instances : 0;
   // chain 0: state1 with kAllPassFilter2 on (low+high); chain 1: state2 with kAllPassFilter1 on (low-high)
-  const unsigned c0 = chain == 0 ? 21333u : 6418u, c1 = chain == 0 ? 49062u : 36982u,
-                 c2 = chain == 0 ? 63010u : 57261u;
+  const int c0 = chain == 0 ? 21333 : 6418, c1 = chain == 0 ? 49062 : 36982, c2 = chain == 0 ? 63010 : 57261;
   int st[6] = {0, 0, 0, 0, 0, 0};
   int32_t* gst = nullptr;
   if (live) {
@@ -166,14 +195,33 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
 #pragma unroll
     for (int i = 0; i < 6; ++i) st[i] = gst[i];
   }
-  for (int f = 0; f < p.frames; ++f) {
-    const int16_t* lo = (live && p.low[inst]) ? p.low[inst] + (size_t)sidx * p.low_stream_stride[inst] + (size_t)f * p.low_frame_stride[inst] : nullptr;
-    const int16_t* hi = (live && p.high[inst]) ? p.high[inst] + (size_t)sidx * p.high_stream_stride[inst] + (size_t)f * p.high_frame_stride[inst] : nullptr;
-    int16_t* out = live ? p.out[inst] + (size_t)sidx * p.out_stream_stride[inst] + (size_t)f * p.out_frame_stride[inst] : nullptr;
-    for (int i0 = 0; i0 < p.band_len; i0 += 8) {
-      uint4 lw = make_uint4(0u, 0u, 0u, 0u), hw = make_uint4(0u, 0u, 0u, 0u);
-      if (lo) lw = *reinterpret_cast<const uint4*>(lo + i0);
-      if (hi) hw = *reinterpret_cast<const uint4*>(hi + i0);
+  const int gpf = p.band_len / 8;             // groups of 8 low + 8 high samples per frame (20 / 40)
+  const int total = p.frames * gpf;           // multiple of kQmfDepth
+  const int16_t* lo_base = (live && p.low[inst]) ? p.low[inst] + (size_t)sidx * p.low_stream_stride[inst] : nullptr;
+  const int16_t* hi_base = (live && p.high[inst]) ? p.high[inst] + (size_t)sidx * p.high_stream_stride[inst] : nullptr;
+  int16_t* out_base = live ? p.out[inst] + (size_t)sidx * p.out_stream_stride[inst] : nullptr;
+  const long long lo_fs = p.low_frame_stride[inst], hi_fs = p.high_frame_stride[inst], out_fs = p.out_frame_stride[inst];
+  uint4 ql[kQmfDepth], qh[kQmfDepth];
+  int fetch_i = 0, store_i = 0;
+  const int16_t* lo_row = lo_base;
+  const int16_t* hi_row = hi_base;
+  int16_t* out_row = out_base;
+  auto fetch = [&](int g, uint4& l, uint4& h) {
+    l = h = make_uint4(0u, 0u, 0u, 0u);
+    if (g < total) {
+      if (lo_base) l = *reinterpret_cast<const uint4*>(lo_row + 8 * fetch_i);
+      if (hi_base) h = *reinterpret_cast<const uint4*>(hi_row + 8 * fetch_i);
+    }
+    if (++fetch_i == gpf) { fetch_i = 0; lo_row += lo_fs; hi_row += hi_fs; }
+  };
+#pragma unroll
+  for (int d = 0; d < kQmfDepth; ++d) fetch(d, ql[d], qh[d]);
+  for (int g0 = 0; g0 < total; g0 += kQmfDepth) {
+#pragma unroll
+    for (int d = 0; d < kQmfDepth; ++d) {
+      const int g = g0 + d;
+      const uint4 lw = ql[d], hw = qh[d];
+      fetch(g + kQmfDepth, ql[d], qh[d]);
       const uint32_t l[4] = {lw.x, lw.y, lw.z, lw.w}, h[4] = {hw.x, hw.y, hw.z, hw.w};
       uint32_t ow[8];
 #pragma unroll
@@ -189,10 +237,12 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
         ow[k] = ((uint32_t)even & 0xffffu) | ((uint32_t)odd << 16);
       }
       // the pair of lanes holds the same 8 words: chain 0 stores the first half
-      if (out) {
-        if (chain == 0) *reinterpret_cast<uint4*>(out + 2 * i0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        else *reinterpret_cast<uint4*>(out + 2 * i0 + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      if (out_base) {
+        int16_t* out = out_row + 16 * store_i;
+        if (chain == 0) *reinterpret_cast<uint4*>(out) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        else *reinterpret_cast<uint4*>(out + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
       }
+      if (++store_i == gpf) { store_i = 0; out_row += out_fs; }
     }
   }
   if (live) {
@@ -229,13 +279,90 @@ constexpr int kResampleKernelWords = 33 * 33 + 3;        // padded rows, 16-byte
 constexpr int kResampleEWords = 64 + 640 + 32;
 constexpr size_t kResampleSmemBytes =
     sizeof(float) * (kResampleKernelWords + kResampleWarpsPerCta * kResampleEWords);
+constexpr size_t kResampleUpSmemBytes = sizeof(float) * (kResampleWarpsPerCta * (64 + 480));
 
-template <bool UP>
+// 480 -> 640: positions are e_n = 31.5 + 0.75 n, so only table rows 0, 8, 16, 24
+// are ever used and the interpolation factor is exactly 0.  The four rows live in constant
+// memory: every tap is an FMUL with a constant-bank operand, no load at all.
+__constant__ float c_up_rows[4][32];
+
+// Lane owns the 20 consecutive outputs n = 20 lane + t: their windows start at
+// E[15 lane + ((126 + 3t) >> 2)], so 46 input samples held in registers serve all 20 outputs
+// (46 conflict-free LDS per lane and frame instead of 640).  The next frame's PCM is fetched
+// into registers while the current one is filtered.
 __global__ void __launch_bounds__(kResampleWarpsPerCta * 32)
-resample_kernel(const ResampleLaunch p) {
-  constexpr int SRC = UP ? 480 : 640;
-  constexpr int DST = UP ? 640 : 480;
-  constexpr int NOUT = DST / 32;         // outputs per lane: 20 / 15
+resample_up_kernel(const ResampleLaunch p) {
+  extern __shared__ float4 rs_smem4[];
+  float* smem = reinterpret_cast<float*>(rs_smem4);
+  const int lane = lane_id(), warp = (int)(threadIdx.x >> 5);
+  const int sidx = (int)blockIdx.x * kResampleWarpsPerCta + warp;
+  if (sidx >= p.n_streams) return;
+  float* E = smem + warp * (64 + 480);
+  int32_t* gst = p.state + (size_t)p.slots[sidx] * kBandStateWords;
+  int16_t* ghist = reinterpret_cast<int16_t*>(gst + kBandOffAnaHist);
+  for (int i = lane; i < 64; i += 32) E[i] = (float)ghist[i];
+  const int16_t* in = p.in + (size_t)sidx * p.in_stream_stride;
+  int16_t* out = p.out + (size_t)sidx * p.out_stream_stride;
+  constexpr int kW = 8;   // 240 words per frame over 32 lanes
+  uint32_t nxt[kW];
+  auto fetch = [&](int f) {
+#pragma unroll
+    for (int u = 0; u < kW; ++u) {
+      const int w = lane + 32 * u;
+      nxt[u] = (f < p.frames && w < 240) ? reinterpret_cast<const uint32_t*>(in + (size_t)f * p.in_frame_stride)[w] : 0u;
+    }
+  };
+  fetch(0);
+  for (int f = 0; f < p.frames; ++f) {
+#pragma unroll
+    for (int u = 0; u < kW; ++u) {
+      const int w = lane + 32 * u;
+      if (w < 240)
+        *reinterpret_cast<float2*>(E + 64 + 2 * w) =
+            make_float2((float)(int16_t)(nxt[u] & 0xffffu), (float)(int16_t)(nxt[u] >> 16));
+    }
+    fetch(f + 1);
+    __syncwarp();
+    float x[46];
+#pragma unroll
+    for (int j = 0; j < 46; ++j) x[j] = E[15 * lane + 31 + j];
+    uint32_t packed[10];
+#pragma unroll
+    for (int t = 0; t < 20; ++t) {
+      const int rel = ((126 + 3 * t) >> 2) - 31;        // window start relative to x[0]
+      const int row = (126 + 3 * t) & 3;                // table row 8 * row = c_up_rows[row]
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        a0 += x[rel + i] * c_up_rows[row][i];
+        a1 += x[rel + i + 1] * c_up_rows[row][i + 1];
+        a2 += x[rel + i + 2] * c_up_rows[row][i + 2];
+        a3 += x[rel + i + 3] * c_up_rows[row][i + 3];
+      }
+      // sinc_resampler_sse.cc:42-54 with interpolation factor 0: a*1 + b*0 == a for the finite
+      // sums b of the second kernel (up to the sign of zero, gone after rounding)
+      const int v = band_round_s16((a0 + a2) + (a1 + a3));
+      if (t & 1) packed[t >> 1] |= (uint32_t)v << 16;
+      else packed[t >> 1] = (uint32_t)v & 0xffffu;
+    }
+    uint2* dst = reinterpret_cast<uint2*>(out + (size_t)f * p.out_frame_stride + 20 * lane);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) dst[q] = make_uint2(packed[2 * q], packed[2 * q + 1]);
+    // history: last 64 input samples
+    const float h0 = E[480 + lane], h1 = E[480 + 32 + lane];
+    __syncwarp();
+    E[lane] = h0;
+    E[32 + lane] = h1;
+    __syncwarp();
+  }
+  for (int i = lane; i < 64; i += 32) ghist[i] = (int16_t)E[i];
+}
+
+// 640 -> 480: warp per stream, lanes over outputs n = lane + 32 t; the schedule and the PCM of the
+// next frame are fetched into registers while the current frame is filtered.
+__global__ void __launch_bounds__(kResampleWarpsPerCta * 32)
+resample_down_kernel(const ResampleLaunch p) {
+  constexpr int SRC = 640, DST = 480, NOUT = DST / 32;   // 15 outputs per lane
   extern __shared__ float4 rs_smem4[];
   float* smem = reinterpret_cast<float*>(rs_smem4);
   float* s_kernel = smem;                                  // 33 rows of 32 taps, row stride 33 (banks)
@@ -249,40 +376,47 @@ resample_kernel(const ResampleLaunch p) {
   float* E = smem + kResampleKernelWords + warp * kResampleEWords;
 
   int32_t* gst = p.state + (size_t)p.slots[sidx] * kBandStateWords;
-  int16_t* ghist = reinterpret_cast<int16_t*>(gst + (UP ? kBandOffAnaHist : kBandOffSynHist));
+  int16_t* ghist = reinterpret_cast<int16_t*>(gst + kBandOffSynHist);
   for (int i = lane; i < 64; i += 32) E[i] = (float)ghist[i];
-  __syncwarp();
-
-  for (int f = 0; f < p.frames; ++f) {
-    const int16_t* in = p.in + (size_t)sidx * p.in_stream_stride + (size_t)f * p.in_frame_stride;
-    int16_t* out = p.out + (size_t)sidx * p.out_stream_stride + (size_t)f * p.out_frame_stride;
-    for (int w = lane; w < SRC / 2; w += 32) {
-      const uint32_t v = reinterpret_cast<const uint32_t*>(in)[w];
-      E[64 + 2 * w] = (float)(int16_t)(v & 0xffffu);
-      E[64 + 2 * w + 1] = (float)(int16_t)(v >> 16);
+  const int16_t* in = p.in + (size_t)sidx * p.in_stream_stride;
+  int16_t* outp = p.out + (size_t)sidx * p.out_stream_stride;
+  constexpr int kW = SRC / 64;   // 10 words per lane
+  uint32_t nxt[kW];
+  int32_t sch[NOUT][3];
+  auto fetch = [&](int f) {
+    if (f < p.frames) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)f * p.in_frame_stride);
+#pragma unroll
+      for (int u = 0; u < kW; ++u) nxt[u] = src[lane + 32 * u];
+      const int32_t* sp = p.schedule + (size_t)f * DST * 3;
+#pragma unroll
+      for (int t = 0; t < NOUT; ++t) {
+        const int n = lane + 32 * t;
+        sch[t][0] = sp[3 * n];
+        sch[t][1] = sp[3 * n + 1];
+        sch[t][2] = sp[3 * n + 2];
+      }
     }
+  };
+  fetch(0);
+  for (int f = 0; f < p.frames; ++f) {
+    int16_t* out = outp + (size_t)f * p.out_frame_stride;
+#pragma unroll
+    for (int u = 0; u < kW; ++u) {
+      const int w = lane + 32 * u;
+      *reinterpret_cast<float2*>(E + 64 + 2 * w) =
+          make_float2((float)(int16_t)(nxt[u] & 0xffffu), (float)(int16_t)(nxt[u] >> 16));
+    }
+    int32_t cur[NOUT][3];
+#pragma unroll
+    for (int t = 0; t < NOUT; ++t) { cur[t][0] = sch[t][0]; cur[t][1] = sch[t][1]; cur[t][2] = sch[t][2]; }
+    fetch(f + 1);
     __syncwarp();
-    const int32_t* sch = UP ? nullptr : p.schedule + (size_t)f * 480 * 3;
-#pragma unroll 1
+#pragma unroll
     for (int t = 0; t < NOUT; ++t) {
       const int n = lane + 32 * t;
-      int epos, off;
-      float fac, fac1;
-      if (UP) {
-        // e_n = 31.5 + 0.75 n  ->  4 e_n = 126 + 3 n; remainders are multiples of 1/4,
-        // so the table row is exact and the interpolation factor is 0
-        const int q4 = 126 + 3 * n;
-        epos = q4 >> 2;
-        off = (q4 & 3) * 8;
-        fac = 0.f;
-        fac1 = 1.f;
-      } else {
-        const int pk = sch[3 * n];
-        epos = pk >> 8;
-        off = pk & 0xff;
-        fac = __int_as_float(sch[3 * n + 1]);
-        fac1 = __int_as_float(sch[3 * n + 2]);
-      }
+      const int epos = cur[t][0] >> 8, off = cur[t][0] & 0xff;
+      const float fac = __int_as_float(cur[t][1]), fac1 = __int_as_float(cur[t][2]);
       const float* k1 = s_kernel + off * 33;
       const float* k2 = k1 + 33;
       const float* x = E + epos;
@@ -301,12 +435,11 @@ resample_kernel(const ResampleLaunch p) {
       // sinc_resampler_sse.cc:42-54
       const float t0 = a0 * fac1 + b0 * fac, t1 = a1 * fac1 + b1 * fac;
       const float t2 = a2 * fac1 + b2 * fac, t3 = a3 * fac1 + b3 * fac;
-      const float res = (t0 + t2) + (t1 + t3);
-      out[n] = (int16_t)band_round_s16(res);
+      out[n] = (int16_t)band_round_s16((t0 + t2) + (t1 + t3));
     }
     __syncwarp();
     // history: last 64 input samples
-    float h0 = E[SRC + lane], h1 = E[SRC + 32 + lane];
+    const float h0 = E[SRC + lane], h1 = E[SRC + 32 + lane];
     __syncwarp();
     E[lane] = h0;
     E[32 + lane] = h1;
@@ -316,6 +449,14 @@ resample_kernel(const ResampleLaunch p) {
 }
 
 // ---- launch helpers (host) -------------------------------------------------------
+// The band path is a chain of stages around the suppressor, each a kernel that walks the frames
+// of its streams serially (filter / resampler state in registers).  Stage s of frames [f0, f0+nf)
+// needs stage s-1 of the same frames and stage s of the frames before; the host layer
+// (ns_capi.cu, RunDevice) issues chunks of frames through one CUDA stream per stage so that the
+// stages of neighbouring chunks overlap.
+//   48 kHz: 0 resample 480->640 | 1 QMF analysis 64k->2x32k | 2 QMF analysis 2x32k->3 bands |
+//           3 NS | 4 QMF synthesis bands->2x32k | 5 QMF synthesis ->64k | 6 resample 640->480
+//   32 kHz: 0 QMF analysis | 1 NS | 2 QMF synthesis
 struct BandLaunch {
   int32_t* state;
   const int* slots;
@@ -325,117 +466,142 @@ struct BandLaunch {
   // position schedule (normally one group = the whole batch)
   struct DownGroup { const int32_t* schedule; const int* stream_index; int count; };
   std::vector<DownGroup> down_groups;
-  int16_t* full;              // full-band PCM [stream][frame][fs/100]
-  long long full_stride;
+  const int16_t* full_in;     // full-band PCM [stream][frame][fs/100]
+  long long full_in_stride;
+  int16_t* full_out;
+  long long full_out_stride;
   int16_t* bands;             // [stream][frame][nb][160]
   long long bands_stride;
   int16_t* scratch;           // 48 kHz: [2][stream][frame][640]
-  int n_streams, frames;
+  int n_streams, frames;      // frames = all frames of the call (scratch layout)
 };
+
+inline int BandStages(int nb) { return nb == 3 ? 7 : 3; }
+inline int BandNsStage(int nb) { return nb == 3 ? 3 : 1; }
 
 inline size_t BandScratchElems(int nb, int n_streams, int frames) {
   return nb == 3 ? (size_t)2 * n_streams * frames * 640 : 0;
 }
 
-inline int LaunchBandSplit(int nb, const BandLaunch& b, cudaStream_t st, uint64_t* launches) {
-  const int n = b.n_streams, F = b.frames;
+// Launches band stage `stage` (not the NS stage) for frames [f0, f0 + nf).
+inline int LaunchBandStage(int nb, const BandLaunch& b, int stage, int f0, int nf, cudaStream_t st,
+                           uint64_t* launches) {
+  const int n = b.n_streams;
   const long long bs = b.bands_stride, fstride = nb * 160;
+  int16_t* bands = b.bands + (size_t)f0 * fstride;
+  const int16_t* fin = b.full_in + (size_t)f0 * (nb == 3 ? 480 : 320);
+  int16_t* fout = b.full_out + (size_t)f0 * (nb == 3 ? 480 : 320);
+  const int qgrid1 = (2 * n + 127) / 128, qgrid2 = (4 * n + 127) / 128;
   if (nb == 2) {
-    QmfAnaLaunch q = {};
-    q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = F; q.instances = 1; q.len = 320;
-    q.state_off[0] = kBandOffQmf0;
-    q.in[0] = b.full; q.in_stream_stride[0] = b.full_stride; q.in_frame_stride[0] = 320;
-    q.low[0] = b.bands; q.low_stream_stride[0] = bs; q.low_frame_stride[0] = fstride;
-    q.high[0] = b.bands + 160; q.high_stream_stride[0] = bs; q.high_frame_stride[0] = fstride;
-    qmf_analysis_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(q);
+    if (stage == 0) {
+      QmfAnaLaunch q = {};
+      q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = nf; q.instances = 1; q.len = 320;
+      q.state_off[0] = kBandOffQmf0;
+      q.in[0] = fin; q.in_stream_stride[0] = b.full_in_stride; q.in_frame_stride[0] = 320;
+      q.low[0] = bands; q.low_stream_stride[0] = bs; q.low_frame_stride[0] = fstride;
+      q.high[0] = bands + 160; q.high_stream_stride[0] = bs; q.high_frame_stride[0] = fstride;
+      qmf_analysis_kernel<<<qgrid1, 128, 0, st>>>(q);
+    } else if (stage == 2) {
+      QmfSynLaunch q = {};
+      q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = nf; q.instances = 1; q.band_len = 160;
+      q.state_off[0] = kBandOffQmf0 + 12;
+      q.low[0] = bands; q.high[0] = bands + 160;
+      q.low_stream_stride[0] = q.high_stream_stride[0] = bs;
+      q.low_frame_stride[0] = q.high_frame_stride[0] = fstride;
+      q.out[0] = fout; q.out_stream_stride[0] = b.full_out_stride; q.out_frame_stride[0] = 320;
+      qmf_synthesis_kernel<<<qgrid1, 128, 0, st>>>(q);
+    } else {
+      return -1;
+    }
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
   if (nb != 3) return -1;
-  int16_t* s64 = b.scratch;                                  // resampled 64 kHz signal
-  int16_t* s32 = b.scratch + (size_t)n * F * 640;            // [stream][frame][low 320 | high 320]
-  const long long ss = (long long)F * 640;
-  ResampleLaunch r = {};
-  r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_up; r.in = b.full; r.out = s64;
-  r.in_stream_stride = b.full_stride; r.in_frame_stride = 480; r.out_stream_stride = ss; r.out_frame_stride = 640;
-  r.n_streams = n; r.frames = F;
-  const size_t smem = kResampleSmemBytes;
-  resample_kernel<true><<<(n + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta, kResampleWarpsPerCta * 32, smem, st>>>(r);
-  ++*launches;
-  QmfAnaLaunch q = {};
-  q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = F; q.instances = 1; q.len = 640;
-  q.state_off[0] = kBandOffQmf0;
-  q.in[0] = s64; q.in_stream_stride[0] = ss; q.in_frame_stride[0] = 640;
-  q.low[0] = s32; q.low_stream_stride[0] = ss; q.low_frame_stride[0] = 640;
-  q.high[0] = s32 + 320; q.high_stream_stride[0] = ss; q.high_frame_stride[0] = 640;
-  qmf_analysis_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(q);
-  ++*launches;
-  QmfAnaLaunch q2 = {};
-  q2.state = b.state; q2.slots = b.slots; q2.n_streams = n; q2.frames = F; q2.instances = 2; q2.len = 320;
-  q2.state_off[0] = kBandOffQmf1; q2.state_off[1] = kBandOffQmf2;
-  q2.in[0] = s32; q2.in[1] = s32 + 320;
-  for (int i = 0; i < 2; ++i) { q2.in_stream_stride[i] = ss; q2.in_frame_stride[i] = 640; }
-  q2.low[0] = b.bands; q2.high[0] = b.bands + 160;           // 0-8 kHz, 8-16 kHz
-  q2.low[1] = nullptr; q2.high[1] = b.bands + 320;           // (24-32 kHz dropped), 16-24 kHz
-  for (int i = 0; i < 2; ++i) {
-    q2.low_stream_stride[i] = q2.high_stream_stride[i] = bs;
-    q2.low_frame_stride[i] = q2.high_frame_stride[i] = fstride;
-  }
-  qmf_analysis_kernel<<<(4 * n + 127) / 128, 128, 0, st>>>(q2);
-  ++*launches;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
-inline int LaunchBandMerge(int nb, const BandLaunch& b, cudaStream_t st, uint64_t* launches) {
-  const int n = b.n_streams, F = b.frames;
-  const long long bs = b.bands_stride, fstride = nb * 160;
-  if (nb == 2) {
-    QmfSynLaunch q = {};
-    q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = F; q.instances = 1; q.band_len = 160;
-    q.state_off[0] = kBandOffQmf0 + 12;
-    q.low[0] = b.bands; q.high[0] = b.bands + 160;
-    q.low_stream_stride[0] = q.high_stream_stride[0] = bs;
-    q.low_frame_stride[0] = q.high_frame_stride[0] = fstride;
-    q.out[0] = b.full; q.out_stream_stride[0] = b.full_stride; q.out_frame_stride[0] = 320;
-    qmf_synthesis_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(q);
-    ++*launches;
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-  }
-  if (nb != 3) return -1;
-  int16_t* s64 = b.scratch;
-  int16_t* s32 = b.scratch + (size_t)n * F * 640;
-  const long long ss = (long long)F * 640;
-  QmfSynLaunch q2 = {};
-  q2.state = b.state; q2.slots = b.slots; q2.n_streams = n; q2.frames = F; q2.instances = 2; q2.band_len = 160;
-  q2.state_off[0] = kBandOffQmf1 + 12; q2.state_off[1] = kBandOffQmf2 + 12;
-  q2.low[0] = b.bands; q2.high[0] = b.bands + 160;
-  q2.low[1] = nullptr; q2.high[1] = b.bands + 320;           // zero low half (splitting_filter.cc:143-145,152)
-  for (int i = 0; i < 2; ++i) {
-    q2.low_stream_stride[i] = q2.high_stream_stride[i] = bs;
-    q2.low_frame_stride[i] = q2.high_frame_stride[i] = fstride;
-    q2.out_stream_stride[i] = ss; q2.out_frame_stride[i] = 640;
-  }
-  q2.out[0] = s32; q2.out[1] = s32 + 320;
-  qmf_synthesis_kernel<<<(4 * n + 127) / 128, 128, 0, st>>>(q2);
-  ++*launches;
-  QmfSynLaunch q = {};
-  q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = F; q.instances = 1; q.band_len = 320;
-  q.state_off[0] = kBandOffQmf0 + 12;
-  q.low[0] = s32; q.high[0] = s32 + 320;
-  q.low_stream_stride[0] = q.high_stream_stride[0] = ss;
-  q.low_frame_stride[0] = q.high_frame_stride[0] = 640;
-  q.out[0] = s64; q.out_stream_stride[0] = ss; q.out_frame_stride[0] = 640;
-  qmf_synthesis_kernel<<<(2 * n + 127) / 128, 128, 0, st>>>(q);
-  ++*launches;
-  for (const BandLaunch::DownGroup& g : b.down_groups) {
-    ResampleLaunch r = {};
-    r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_down; r.schedule = g.schedule;
-    r.stream_index = g.stream_index; r.in = s64; r.out = b.full;
-    r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_stride; r.out_frame_stride = 480;
-    r.n_streams = g.count; r.frames = F;
-    resample_kernel<false><<<(g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta,
-                             kResampleWarpsPerCta * 32, kResampleSmemBytes, st>>>(r);
-    ++*launches;
+  const long long ss = (long long)b.frames * 640;
+  int16_t* s64 = b.scratch + (size_t)f0 * 640;                                   // 64 kHz signal
+  int16_t* s32 = b.scratch + (size_t)n * b.frames * 640 + (size_t)f0 * 640;      // [low 320 | high 320]
+  const int rgrid = (n + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta;
+  switch (stage) {
+    case 0: {
+      ResampleLaunch r = {};
+      r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_up; r.in = fin; r.out = s64;
+      r.in_stream_stride = b.full_in_stride; r.in_frame_stride = 480; r.out_stream_stride = ss; r.out_frame_stride = 640;
+      r.n_streams = n; r.frames = nf;
+      resample_up_kernel<<<rgrid, kResampleWarpsPerCta * 32, kResampleUpSmemBytes, st>>>(r);
+      ++*launches;
+      break;
+    }
+    case 1: {
+      QmfAnaLaunch q = {};
+      q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = nf; q.instances = 1; q.len = 640;
+      q.state_off[0] = kBandOffQmf0;
+      q.in[0] = s64; q.in_stream_stride[0] = ss; q.in_frame_stride[0] = 640;
+      q.low[0] = s32; q.low_stream_stride[0] = ss; q.low_frame_stride[0] = 640;
+      q.high[0] = s32 + 320; q.high_stream_stride[0] = ss; q.high_frame_stride[0] = 640;
+      qmf_analysis_kernel<<<qgrid1, 128, 0, st>>>(q);
+      ++*launches;
+      break;
+    }
+    case 2: {
+      QmfAnaLaunch q2 = {};
+      q2.state = b.state; q2.slots = b.slots; q2.n_streams = n; q2.frames = nf; q2.instances = 2; q2.len = 320;
+      q2.state_off[0] = kBandOffQmf1; q2.state_off[1] = kBandOffQmf2;
+      q2.in[0] = s32; q2.in[1] = s32 + 320;
+      for (int i = 0; i < 2; ++i) { q2.in_stream_stride[i] = ss; q2.in_frame_stride[i] = 640; }
+      q2.low[0] = bands; q2.high[0] = bands + 160;           // 0-8 kHz, 8-16 kHz
+      q2.low[1] = nullptr; q2.high[1] = bands + 320;         // (24-32 kHz dropped), 16-24 kHz
+      for (int i = 0; i < 2; ++i) {
+        q2.low_stream_stride[i] = q2.high_stream_stride[i] = bs;
+        q2.low_frame_stride[i] = q2.high_frame_stride[i] = fstride;
+      }
+      qmf_analysis_kernel<<<qgrid2, 128, 0, st>>>(q2);
+      ++*launches;
+      break;
+    }
+    case 4: {
+      QmfSynLaunch q2 = {};
+      q2.state = b.state; q2.slots = b.slots; q2.n_streams = n; q2.frames = nf; q2.instances = 2; q2.band_len = 160;
+      q2.state_off[0] = kBandOffQmf1 + 12; q2.state_off[1] = kBandOffQmf2 + 12;
+      q2.low[0] = bands; q2.high[0] = bands + 160;
+      q2.low[1] = nullptr; q2.high[1] = bands + 320;         // zero low half (splitting_filter.cc:143-145,152)
+      for (int i = 0; i < 2; ++i) {
+        q2.low_stream_stride[i] = q2.high_stream_stride[i] = bs;
+        q2.low_frame_stride[i] = q2.high_frame_stride[i] = fstride;
+        q2.out_stream_stride[i] = ss; q2.out_frame_stride[i] = 640;
+      }
+      q2.out[0] = s32; q2.out[1] = s32 + 320;
+      qmf_synthesis_kernel<<<qgrid2, 128, 0, st>>>(q2);
+      ++*launches;
+      break;
+    }
+    case 5: {
+      QmfSynLaunch q = {};
+      q.state = b.state; q.slots = b.slots; q.n_streams = n; q.frames = nf; q.instances = 1; q.band_len = 320;
+      q.state_off[0] = kBandOffQmf0 + 12;
+      q.low[0] = s32; q.high[0] = s32 + 320;
+      q.low_stream_stride[0] = q.high_stream_stride[0] = ss;
+      q.low_frame_stride[0] = q.high_frame_stride[0] = 640;
+      q.out[0] = s64; q.out_stream_stride[0] = ss; q.out_frame_stride[0] = 640;
+      qmf_synthesis_kernel<<<qgrid1, 128, 0, st>>>(q);
+      ++*launches;
+      break;
+    }
+    case 6: {
+      for (const BandLaunch::DownGroup& g : b.down_groups) {
+        ResampleLaunch r = {};
+        r.state = b.state; r.slots = b.slots; r.kernel = b.kernel_down;
+        r.schedule = g.schedule + (size_t)f0 * 480 * 3;
+        r.stream_index = g.stream_index; r.in = s64; r.out = fout;
+        r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_out_stride; r.out_frame_stride = 480;
+        r.n_streams = g.count; r.frames = nf;
+        resample_down_kernel<<<(g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta,
+                                 kResampleWarpsPerCta * 32, kResampleSmemBytes, st>>>(r);
+        ++*launches;
+      }
+      break;
+    }
+    default:
+      return -1;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -93,6 +94,10 @@ struct DeviceCtx {
   int32_t* d_down_sched = nullptr;     // 48 kHz: resampler schedule of the current launch
   size_t down_sched_words = 0;
   std::vector<cudaEvent_t> events;     // host-pointer batch pipeline (reused across calls)
+  // 32/48 kHz: one CUDA stream per pipeline stage, events between the stages of a chunk
+  cudaStream_t stage_stream[9] = {};
+  cudaEvent_t fork_event = nullptr;
+  std::vector<cudaEvent_t> band_events;
 };
 
 std::vector<DeviceCtx> g_devs;
@@ -163,6 +168,13 @@ int DeviceReady(int dev, DeviceCtx** out) {
       band_make_sinc_kernel(480.0 / 640.0, k.data());
       CU_OK(cudaMalloc(&d.d_sinc_up, sizeof(float) * k.size()));
       CU_OK(cudaMemcpy(d.d_sinc_up, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice));
+      {
+        // the 480 -> 640 resampler only ever uses table rows 16, 8, 0, 24 (band_kernels.cuh)
+        float rows[4][32];
+        const int which[4] = {0, 8, 16, 24};
+        for (int r = 0; r < 4; ++r) memcpy(rows[r], k.data() + which[r] * 32, sizeof(rows[r]));
+        CU_OK(cudaMemcpyToSymbol(c_up_rows, rows, sizeof(rows)));
+      }
       band_make_sinc_kernel(640.0 / 480.0, k.data());
       CU_OK(cudaMalloc(&d.d_sinc_down, sizeof(float) * k.size()));
       CU_OK(cudaMemcpy(d.d_sinc_down, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice));
@@ -438,168 +450,272 @@ int LaunchNsx(int ana, int nb, const NsxLaunch& p, cudaStream_t st) {
 
 int NumBands(uint32_t fs) { return fs == 32000 ? 2 : (fs == 48000 ? 3 : 1); }
 
-// Enqueues split -> NS -> merge for `idx.size()` streams of one device whose
-// full-band int16 PCM sits in device memory.
-int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in,
-              size_t in_stride, int16_t* d_out, size_t out_stride, int frames, cudaStream_t st) {
-  const int n = (int)hs.size();
-  const uint32_t fs = hs[0]->fs;
-  const int nb = NumBands(fs);
-  const int fl = (int)fs / 100;
-  const int ana = fs == 8000 ? 128 : 256;
-  std::vector<int> slots(n), bslots(n);
-  for (int i = 0; i < n; ++i) {
-    slots[i] = hs[i]->slot;
-    bslots[i] = BandSlot(hs[i]);
-  }
-  const int16_t* ns_in = d_in;
-  int16_t* ns_out = d_out;
-  long long ns_in_ss = (long long)in_stride, ns_out_ss = (long long)out_stride;
-  long long fstride = fl, bstride = 0;
-  int* d_bslots = nullptr;
-  if (nb > 1) {
-    // band scratch [stream][frame][band][160], split in place of the NS input
-    const size_t need = (size_t)n * frames * nb * 160;
-    if (need > d.bands_elems) {
-      CU_OK(cudaStreamSynchronize(st));
-      if (d.d_bands) CU_OK(cudaFree(d.d_bands));
-      CU_OK(cudaMalloc(&d.d_bands, sizeof(int16_t) * need));
-      d.bands_elems = need;
-    }
-    const size_t need_s = BandScratchElems(nb, n, frames);
-    if (need_s > d.band_scratch_elems) {
-      CU_OK(cudaStreamSynchronize(st));
-      if (d.d_band_scratch) CU_OK(cudaFree(d.d_band_scratch));
-      CU_OK(cudaMalloc(&d.d_band_scratch, sizeof(int16_t) * need_s));
-      d.band_scratch_elems = need_s;
-    }
-    if ((in_stride | out_stride) & 7) return Fail("strides must be multiples of 8 samples at 32/48 kHz");
-    ns_in = ns_out = d.d_bands;
-    ns_in_ss = ns_out_ss = (long long)frames * nb * 160;
-    fstride = nb * 160;
-    bstride = 160;
-  }
-  // slot lists: [0,n) = NS slots, [n,2n) = band slots
-  std::vector<int> all(slots);
-  if (nb > 1) all.insert(all.end(), bslots.begin(), bslots.end());
-  if (UploadSlots(d, all, st) != 0) return -1;
-  d_bslots = d.d_slots + n;
+// Host buffers of a host-pointer batch call at 32/48 kHz: the copies become the first and last
+// stage of the band pipeline below.
+struct HostIo {
+  const int16_t* in;
+  size_t in_stride;
+  int16_t* out;
+  size_t out_stride;
+};
 
-  if (nb > 1) {
-    BandLaunch b;
-    b.state = (int32_t*)d.b_state.base;
-    b.slots = d_bslots;
-    b.full = const_cast<int16_t*>(d_in);
-    b.full_stride = (long long)in_stride;
-    b.bands = d.d_bands;
-    b.bands_stride = ns_in_ss;
-    b.n_streams = n;
-    b.frames = frames;
-    b.kernel_up = d.d_sinc_up;
-    b.kernel_down = d.d_sinc_down;
-    b.scratch = d.d_band_scratch;
-    if (LaunchBandSplit(nb, b, st, &g_launches) != 0) return Fail("band split launch failed");
-  }
+constexpr int kBandMaxStages = 9;        // copy-in | 7 band / NS stages | copy-out
+constexpr int kBandBlockFrames = 100;    // frames per pipelined block (bounds the scratch: ~5.4 KB per stream-frame)
+
+// NS launch over the whole batch, frames [f0, f0 + nf) of PCM laid out with the given strides.
+int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t* in, long long in_ss,
+             int16_t* out, long long out_ss, long long fstride, long long bstride, int f0, int nf, cudaStream_t s) {
   if (magic == kMagicF) {
     NsfLaunch p;
     p.state = (float*)d.f_state.base;
     p.hist = (int*)d.f_hist.base;
     p.slots = d.d_slots;
     p.tables = d.d_nsf_tables;
-    p.in = ns_in;
-    p.out = ns_out;
-    p.in_stream_stride = ns_in_ss;
-    p.out_stream_stride = ns_out_ss;
+    p.in = in + (size_t)f0 * fstride;
+    p.out = out + (size_t)f0 * fstride;
+    p.in_stream_stride = in_ss;
+    p.out_stream_stride = out_ss;
     p.in_frame_stride = p.out_frame_stride = fstride;
     p.in_band_stride = p.out_band_stride = bstride;
     p.n_streams = n;
-    p.frames = frames;
-    if (LaunchNsf(ana, nb, true, p, st) != 0) return -1;
-  } else {
-    NsxLaunch p;
-    p.state = (uint32_t*)d.x_state.base;
-    p.slots = d.d_slots;
-    p.tables = d.d_nsx_tables;
-    p.in = ns_in;
-    p.out = ns_out;
-    p.in_stream_stride = ns_in_ss;
-    p.out_stream_stride = ns_out_ss;
-    p.in_frame_stride = p.out_frame_stride = fstride;
-    p.in_band_stride = p.out_band_stride = bstride;
-    p.n_streams = n;
-    p.frames = frames;
-    if (LaunchNsx(ana, nb, p, st) != 0) return -1;
+    p.frames = nf;
+    return LaunchNsf(ana, nb, true, p, s);
   }
-  if (nb > 1) {
-    BandLaunch b;
-    b.state = (int32_t*)d.b_state.base;
-    b.slots = d_bslots;
-    b.full = d_out;
-    b.full_stride = (long long)out_stride;
-    b.bands = d.d_bands;
-    b.bands_stride = ns_in_ss;
-    b.n_streams = n;
-    b.frames = frames;
-    b.kernel_up = d.d_sinc_up;
-    b.kernel_down = d.d_sinc_down;
-    b.scratch = d.d_band_scratch;
-    if (nb == 3) {
-      // 640 -> 480 resampler positions: replay the reference's running double per distinct
-      // starting value, group streams whose schedules coincide (streams of different age differ
-      // by ~1e-13 in position, which almost never changes a table row or a float weight)
-      const size_t words = (size_t)frames * 480 * 3;
-      std::vector<std::vector<int32_t>> scheds;
-      std::vector<std::vector<int>> members;
-      std::vector<std::pair<double, std::pair<int, double>>> seen;   // start -> (group, end)
-      for (int i = 0; i < n; ++i) {
-        const double v0 = hs[i]->down_vsi;
-        int gi = -1;
-        double vend = 0;
-        for (auto& s : seen)
-          if (memcmp(&s.first, &v0, sizeof(double)) == 0) { gi = s.second.first; vend = s.second.second; break; }
+  NsxLaunch p;
+  p.state = (uint32_t*)d.x_state.base;
+  p.slots = d.d_slots;
+  p.tables = d.d_nsx_tables;
+  p.in = in + (size_t)f0 * fstride;
+  p.out = out + (size_t)f0 * fstride;
+  p.in_stream_stride = in_ss;
+  p.out_stream_stride = out_ss;
+  p.in_frame_stride = p.out_frame_stride = fstride;
+  p.in_band_stride = p.out_band_stride = bstride;
+  p.n_streams = n;
+  p.frames = nf;
+  return LaunchNsx(ana, nb, p, s);
+}
+
+// One block of <= kBandBlockFrames frames through the 32/48 kHz chain.
+//
+// Every stage kernel walks the frames of its streams serially with filter / resampler state in
+// registers, so a stage's duration is set by per-stream latency, not by how many streams it
+// carries (measured: 512 and 2048 streams take the same 4.4 ms for 50 frames end to end).  The
+// block is therefore cut into chunks of a few frames that flow through one CUDA stream per
+// stage: stage s of chunk c waits for stage s-1 of chunk c (event) and for stage s of chunk c-1
+// (stream order), and the stages of neighbouring chunks overlap on the otherwise idle SMs.
+// With `host`, the H2D and D2H copies are two more stages of the same pipeline.
+int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in, size_t in_stride,
+                 int16_t* d_out, size_t out_stride, int frames, cudaStream_t st, const HostIo* host) {
+  const int n = (int)hs.size();
+  const uint32_t fs = hs[0]->fs;
+  const int nb = NumBands(fs);
+  const int fl = (int)fs / 100;
+  const int* d_bslots = d.d_slots + n;
+
+  // band scratch [stream][frame][band][160], split in place of the NS input
+  const size_t need = (size_t)n * frames * nb * 160;
+  if (need > d.bands_elems) {
+    CU_OK(cudaDeviceSynchronize());
+    if (d.d_bands) CU_OK(cudaFree(d.d_bands));
+    CU_OK(cudaMalloc(&d.d_bands, sizeof(int16_t) * need));
+    d.bands_elems = need;
+  }
+  const size_t need_s = BandScratchElems(nb, n, frames);
+  if (need_s > d.band_scratch_elems) {
+    CU_OK(cudaDeviceSynchronize());
+    if (d.d_band_scratch) CU_OK(cudaFree(d.d_band_scratch));
+    CU_OK(cudaMalloc(&d.d_band_scratch, sizeof(int16_t) * need_s));
+    d.band_scratch_elems = need_s;
+  }
+  const long long bands_ss = (long long)frames * nb * 160;
+
+  BandLaunch bl;
+  bl.state = (int32_t*)d.b_state.base;
+  bl.slots = d_bslots;
+  bl.kernel_up = d.d_sinc_up;
+  bl.kernel_down = d.d_sinc_down;
+  bl.full_in = d_in;
+  bl.full_in_stride = (long long)in_stride;
+  bl.full_out = d_out;
+  bl.full_out_stride = (long long)out_stride;
+  bl.bands = d.d_bands;
+  bl.bands_stride = bands_ss;
+  bl.scratch = d.d_band_scratch;
+  bl.n_streams = n;
+  bl.frames = frames;
+
+  // 48 kHz merge: 640 -> 480 resampler positions.  Replay the reference's running double per
+  // distinct starting value and group the streams whose schedules coincide (streams of different
+  // age differ by ~1e-13 in position, which almost never changes a table row or a float weight).
+  if (nb == 3) {
+    const size_t words = (size_t)frames * 480 * 3;
+    std::vector<std::vector<int32_t>> scheds;
+    std::vector<std::vector<int>> members;
+    std::vector<std::pair<double, std::pair<int, double>>> seen;   // start -> (schedule, end)
+    for (int i = 0; i < n; ++i) {
+      const double v0 = hs[i]->down_vsi;
+      int gi = -1;
+      double vend = 0;
+      for (auto& sn : seen)
+        if (memcmp(&sn.first, &v0, sizeof(double)) == 0) { gi = sn.second.first; vend = sn.second.second; break; }
+      if (gi < 0) {
+        std::vector<int32_t> sc(words);
+        double v = v0;
+        band_down_schedule(&v, frames, sc.data());
+        vend = v;
+        for (size_t g = 0; g < scheds.size(); ++g)
+          if (memcmp(scheds[g].data(), sc.data(), words * sizeof(int32_t)) == 0) { gi = (int)g; break; }
         if (gi < 0) {
-          std::vector<int32_t> sc(words);
-          double v = v0;
-          band_down_schedule(&v, frames, sc.data());
-          vend = v;
-          for (size_t g = 0; g < scheds.size(); ++g)
-            if (memcmp(scheds[g].data(), sc.data(), words * sizeof(int32_t)) == 0) { gi = (int)g; break; }
-          if (gi < 0) {
-            gi = (int)scheds.size();
-            scheds.push_back(std::move(sc));
-            members.emplace_back();
-          }
-          seen.push_back({v0, {gi, vend}});
+          gi = (int)scheds.size();
+          scheds.push_back(std::move(sc));
+          members.emplace_back();
         }
-        members[gi].push_back(i);
-        hs[i]->down_vsi = vend;
+        seen.push_back({v0, {gi, vend}});
       }
-      const size_t need_w = scheds.size() * words + (scheds.size() > 1 ? (size_t)n : 0);
-      if (need_w > d.down_sched_words) {
-        CU_OK(cudaStreamSynchronize(st));
-        if (d.d_down_sched) CU_OK(cudaFree(d.d_down_sched));
-        CU_OK(cudaMalloc(&d.d_down_sched, sizeof(int32_t) * need_w));
-        d.down_sched_words = need_w;
-      }
-      int32_t* d_idx = d.d_down_sched + scheds.size() * words;
-      size_t idx_off = 0;
-      for (size_t g = 0; g < scheds.size(); ++g) {
-        CU_OK(cudaMemcpyAsync(d.d_down_sched + g * words, scheds[g].data(), sizeof(int32_t) * words,
-                              cudaMemcpyHostToDevice, st));
-        BandLaunch::DownGroup dg;
-        dg.schedule = d.d_down_sched + g * words;
-        dg.count = (int)members[g].size();
-        dg.stream_index = nullptr;
-        if (scheds.size() > 1) {
-          CU_OK(cudaMemcpyAsync(d_idx + idx_off, members[g].data(), sizeof(int) * members[g].size(),
-                                cudaMemcpyHostToDevice, st));
-          dg.stream_index = reinterpret_cast<const int*>(d_idx + idx_off);
-          idx_off += members[g].size();
-        }
-        b.down_groups.push_back(dg);
-      }
+      members[gi].push_back(i);
+      hs[i]->down_vsi = vend;
     }
-    if (LaunchBandMerge(nb, b, st, &g_launches) != 0) return Fail("band merge launch failed");
+    const size_t need_w = scheds.size() * words + (scheds.size() > 1 ? (size_t)n : 0);
+    if (need_w > d.down_sched_words) {
+      CU_OK(cudaDeviceSynchronize());
+      if (d.d_down_sched) CU_OK(cudaFree(d.d_down_sched));
+      CU_OK(cudaMalloc(&d.d_down_sched, sizeof(int32_t) * need_w));
+      d.down_sched_words = need_w;
+    }
+    int32_t* d_idx = d.d_down_sched + scheds.size() * words;
+    size_t idx_off = 0;
+    for (size_t g = 0; g < scheds.size(); ++g) {
+      // pageable sources: staged by the runtime before the call returns
+      CU_OK(cudaMemcpyAsync(d.d_down_sched + g * words, scheds[g].data(), sizeof(int32_t) * words,
+                            cudaMemcpyHostToDevice, st));
+      BandLaunch::DownGroup dg;
+      dg.schedule = d.d_down_sched + g * words;
+      dg.count = (int)members[g].size();
+      dg.stream_index = nullptr;
+      if (scheds.size() > 1) {
+        CU_OK(cudaMemcpyAsync(d_idx + idx_off, members[g].data(), sizeof(int) * members[g].size(),
+                              cudaMemcpyHostToDevice, st));
+        dg.stream_index = reinterpret_cast<const int*>(d_idx + idx_off);
+        idx_off += members[g].size();
+      }
+      bl.down_groups.push_back(dg);
+    }
+  }
+
+  // chunk plan: short chunks keep every stage busy (measured at 2048 x 48 kHz, ms per 50-frame
+  // step: 1-4 frames 2.6, 8 frames 2.8, 25 frames 3.3; unpipelined 4.6)
+  int chunk = 4;
+  if (const char* e = getenv("NSB200_BAND_CHUNK")) {
+    const int v = atoi(e);
+    if (v > 0) chunk = v;
+  }
+  if (chunk > frames) chunk = frames;
+  const int nchunks = (frames + chunk - 1) / chunk;
+  const int band_stages = BandStages(nb), ns_stage = BandNsStage(nb);
+  const int first = host ? 1 : 0;                       // pipeline index of band stage 0
+  const int nstages = band_stages + (host ? 2 : 0);
+  if (!d.fork_event) {
+    CU_OK(cudaEventCreateWithFlags(&d.fork_event, cudaEventDisableTiming));
+    for (int k = 0; k < kBandMaxStages; ++k) CU_OK(cudaStreamCreateWithFlags(&d.stage_stream[k], cudaStreamNonBlocking));
+  }
+  while (d.band_events.size() < (size_t)nstages * nchunks) {
+    cudaEvent_t e;
+    CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    d.band_events.push_back(e);
+  }
+  // NSB200_TRACE=2: timeline of the stages of every chunk on stderr (tuning aid)
+  const char* trace_env = getenv("NSB200_TRACE");
+  const bool trace = trace_env && atoi(trace_env) >= 2;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tev.push_back(e);
+  };
+  // every stage stream starts after the caller's stream: inputs are ready and the previous
+  // block has released the scratch
+  CU_OK(cudaEventRecord(d.fork_event, st));
+  for (int k = 0; k < nstages; ++k) CU_OK(cudaStreamWaitEvent(d.stage_stream[k], d.fork_event, 0));
+  mark(d.stage_stream[0]);
+  const int ana = 256;
+  for (int c = 0; c < nchunks; ++c) {
+    const int f0 = c * chunk;
+    const int nf = frames - f0 < chunk ? frames - f0 : chunk;
+    for (int k = 0; k < nstages; ++k) {
+      cudaStream_t s = d.stage_stream[k];
+      if (k > 0) CU_OK(cudaStreamWaitEvent(s, d.band_events[(size_t)c * nstages + k - 1], 0));
+      const int bk = k - first;   // band stage index
+      if (bk < 0) {
+        CU_OK(cudaMemcpy2DAsync(const_cast<int16_t*>(d_in) + (size_t)f0 * fl, in_stride * sizeof(int16_t),
+                                host->in + (size_t)f0 * fl, host->in_stride * sizeof(int16_t),
+                                (size_t)nf * fl * sizeof(int16_t), n, cudaMemcpyHostToDevice, s));
+      } else if (bk == band_stages) {
+        CU_OK(cudaMemcpy2DAsync(host->out + (size_t)f0 * fl, host->out_stride * sizeof(int16_t),
+                                d_out + (size_t)f0 * fl, out_stride * sizeof(int16_t),
+                                (size_t)nf * fl * sizeof(int16_t), n, cudaMemcpyDeviceToHost, s));
+      } else if (bk == ns_stage) {
+        if (LaunchNs(d, magic, ana, nb, n, d.d_bands, bands_ss, d.d_bands, bands_ss, nb * 160, 160, f0, nf, s) != 0)
+          return -1;
+      } else {
+        if (LaunchBandStage(nb, bl, bk, f0, nf, s, &g_launches) != 0) return Fail("band stage launch failed");
+      }
+      CU_OK(cudaEventRecord(d.band_events[(size_t)c * nstages + k], s));
+      mark(s);
+    }
+  }
+  // join: the last stage of the last chunk follows everything else of the block
+  CU_OK(cudaStreamWaitEvent(st, d.band_events[(size_t)(nchunks - 1) * nstages + nstages - 1], 0));
+  if (trace) {
+    CU_OK(cudaDeviceSynchronize());
+    for (int c = 0; c < nchunks; ++c) {
+      fprintf(stderr, "chunk %2d ends:", c);
+      for (int k = 0; k < nstages; ++k) {
+        float t;
+        cudaEventElapsedTime(&t, tev[0], tev[1 + (size_t)c * nstages + k]);
+        fprintf(stderr, " %.3f", t);
+      }
+      fprintf(stderr, " ms\n");
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
+// Enqueues the suppressor (with band split / merge at 32/48 kHz) for the streams of one device.
+// d_in / d_out: full-band int16 PCM in device memory; with `host` (32/48 kHz only) they are
+// staging buffers the pipeline fills from / drains to the host buffers itself.
+int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in,
+              size_t in_stride, int16_t* d_out, size_t out_stride, int frames, cudaStream_t st,
+              const HostIo* host = nullptr) {
+  const int n = (int)hs.size();
+  const uint32_t fs = hs[0]->fs;
+  const int nb = NumBands(fs);
+  const int fl = (int)fs / 100;
+  // slot lists: [0,n) = NS slots, [n,2n) = band slots
+  std::vector<int> all(nb > 1 ? 2 * (size_t)n : (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    all[i] = hs[i]->slot;
+    if (nb > 1) all[n + i] = BandSlot(hs[i]);
+  }
+  if (UploadSlots(d, all, st) != 0) return -1;
+  if (nb == 1)
+    return LaunchNs(d, magic, fs == 8000 ? 128 : 256, 1, n, d_in, (long long)in_stride, d_out, (long long)out_stride,
+                    fl, 0, 0, frames, st);
+  if ((in_stride | out_stride) & 7) return Fail("strides must be multiples of 8 samples at 32/48 kHz");
+  for (int f0 = 0; f0 < frames; f0 += kBandBlockFrames) {
+    const int nf = frames - f0 < kBandBlockFrames ? frames - f0 : kBandBlockFrames;
+    HostIo h;
+    if (host) {
+      h = *host;
+      h.in += (size_t)f0 * fl;
+      h.out += (size_t)f0 * fl;
+    }
+    if (RunBandBlock(d, magic, hs, d_in + (size_t)f0 * fl, in_stride, d_out + (size_t)f0 * fl, out_stride, nf, st,
+                     host ? &h : nullptr) != 0)
+      return -1;
   }
   return 0;
 }
@@ -652,6 +768,40 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   for (int i = 0; i < n; ++i) {
     if (!runs.empty() && runs.back().dev == hs[i]->dev) runs.back().count++;
     else runs.push_back(Run{hs[i]->dev, i, 1});
+  }
+  if (NumBands(hs[0]->fs) > 1) {
+    // 32/48 kHz: the copies are the first and last stage of the band pipeline (RunBandBlock);
+    // staging holds one block of frames per direction
+    const int block = frames < kBandBlockFrames ? frames : kBandBlockFrames;
+    for (const Run& r : runs) {
+      DeviceCtx* d;
+      if (DeviceReady(r.dev, &d) != 0) return -1;
+      const size_t need = (size_t)r.count * block * fl;
+      if (need > d->stage_elems) {
+        CU_OK(cudaDeviceSynchronize());
+        if (d->d_in) { CU_OK(cudaFree(d->d_in)); CU_OK(cudaFree(d->d_out)); }
+        CU_OK(cudaMalloc(&d->d_in, sizeof(int16_t) * need));
+        CU_OK(cudaMalloc(&d->d_out, sizeof(int16_t) * need));
+        d->stage_elems = need;
+      }
+    }
+    for (int f0 = 0; f0 < frames; f0 += block) {
+      const int nf = frames - f0 < block ? frames - f0 : block;
+      for (const Run& r : runs) {
+        DeviceCtx* d = &g_devs[r.dev];
+        CU_OK(cudaSetDevice(r.dev));
+        std::vector<Handle*> sub(hs.begin() + r.first, hs.begin() + r.first + r.count);
+        HostIo hio = {in + (size_t)r.first * in_stride + (size_t)f0 * fl, in_stride,
+                      out + (size_t)r.first * out_stride + (size_t)f0 * fl, out_stride};
+        const size_t per = (size_t)block * fl;
+        if (RunDevice(*d, magic, sub, d->d_in, per, d->d_out, per, nf, d->stream, &hio) != 0) return -1;
+      }
+    }
+    for (const Run& r : runs) {
+      CU_OK(cudaSetDevice(r.dev));
+      CU_OK(cudaStreamSynchronize(g_devs[r.dev].stream));
+    }
+    return 0;
   }
   // chunking: the copies bound the call (PCIe, ~50 GB/s each way, full duplex) as soon as the
   // kernel keeps up, so the pipeline wants many small chunks -- fill and drain cost one chunk of

@@ -79,3 +79,70 @@ def test_48k_streams_of_different_age_in_one_batch(nslib, reflib):
         assert np.array_equal(ob[s], reflib.nsx(fs, mode, x[s][:rest * fl]))
     for i in range(n):
         lib.WebRtcNsx_Free(hs[i])
+
+
+@pytest.mark.parametrize("fs", [32000, 48000])
+def test_full_scale_square_waves_bit_exact(nslib, reflib, fs):
+    """Worst-case inputs for the all-pass QMF recurrences: full-scale +-32768/32767 sequences
+    (random signs, square waves at several periods).  The kernels drop the reference's saturating
+    subtract because it provably never acts (band_kernels.cuh, band_allpass3); this is the input
+    class that would expose it if the bound were wrong."""
+    n, frames, fl = 8, 120, fs // 100
+    rng = np.random.default_rng(7)
+    x = np.empty((n, frames * fl), dtype=np.int16)
+    t = np.arange(frames * fl)
+    for s in range(n):
+        if s < 3:
+            sign = rng.integers(0, 2, size=t.size) * 2 - 1
+        else:
+            sign = np.where((t // (s - 2)) % 2 == 0, 1, -1)
+        x[s] = np.where(sign > 0, 32767, -32768).astype(np.int16)
+    b = nslib.NsBatch(n, fs, 1, fixed=True)
+    out = b.process(x)
+    for s in range(n):
+        ref = reflib.nsx(fs, 1, x[s])
+        assert np.array_equal(ref, out[s]), "fs %d stream %d differs first at sample %d" % (
+            fs, s, int(np.nonzero(ref != out[s])[0][0]))
+    b.close()
+
+
+@pytest.mark.parametrize("fs,chunk", [(32000, 1), (32000, 7), (48000, 1), (48000, 3), (48000, 64)])
+def test_frame_chunk_pipeline_bit_exact(nslib, reflib, fs, chunk, monkeypatch):
+    """The 32/48 kHz path cuts a call into chunks of frames that flow through one CUDA stream per
+    stage (ns_capi.cu RunBandBlock), host copies included; forced here to several chunk sizes,
+    with 48 kHz streams of different age so that several resampler schedules are in flight."""
+    import ctypes as C
+    monkeypatch.setenv("NSB200_BAND_CHUNK", str(chunk))
+    mode, fl = 2, fs // 100
+    lib = nslib.load_library()
+    n, head, total = 7, 23, 90
+    x = nslib.synth_pcm_host(n, fs, total * fl)
+    hs = (C.c_void_p * n)()
+    for i in range(n):
+        h = C.c_void_p()
+        assert lib.WebRtcNsx_Create(C.byref(h)) == 0
+        hs[i] = h
+    assert lib.WebRtcNsx_InitBatch(hs, n, fs, mode) == 0
+    # streams 1, 4, 5 run alone first (their resamplers age), then all seven share launches
+    old = [1, 4, 5]
+    sub = (C.c_void_p * len(old))(*[hs[i] for i in old])
+    a = np.ascontiguousarray(x[old, :head * fl])
+    oa = np.zeros_like(a)
+    assert lib.WebRtcNsx_ProcessBatch(sub, len(old), a.ctypes.data_as(C.c_void_p), a.shape[1],
+                                      oa.ctypes.data_as(C.c_void_p), oa.shape[1], head) == 0, lib.WebRtcNsB200_LastError()
+    rest = total - head
+    b = np.ascontiguousarray(np.stack([x[i, head * fl:] if i in old else x[i, :rest * fl] for i in range(n)]))
+    ob = np.zeros_like(b)
+    for f0, nf in [(0, 5), (5, rest - 5)]:
+        bi = np.ascontiguousarray(b[:, f0 * fl:(f0 + nf) * fl])
+        bo = np.zeros_like(bi)
+        assert lib.WebRtcNsx_ProcessBatch(hs, n, bi.ctypes.data_as(C.c_void_p), bi.shape[1],
+                                          bo.ctypes.data_as(C.c_void_p), bo.shape[1], nf) == 0, lib.WebRtcNsB200_LastError()
+        ob[:, f0 * fl:(f0 + nf) * fl] = bo
+    for k, i in enumerate(old):
+        assert np.array_equal(np.concatenate([oa[k], ob[i]]), reflib.nsx(fs, mode, x[i])), "aged stream %d" % i
+    for i in range(n):
+        if i not in old:
+            assert np.array_equal(ob[i], reflib.nsx(fs, mode, x[i][:rest * fl])), "fresh stream %d" % i
+    for i in range(n):
+        lib.WebRtcNsx_Free(hs[i])
