@@ -417,6 +417,8 @@ int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
   const size_t need = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
   const size_t smem = need;
+  if (smem > 48 * 1024)
+    CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nsf_process_kernel<ANA, NB, I16><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -432,10 +434,23 @@ int LaunchNsf(int ana, int nb, bool i16, const NsfLaunch& p, cudaStream_t st) {
 
 template <int ANA, int NB>
 int LaunchNsxT(const NsxLaunch& p, cudaStream_t st) {
-  const int grid = (p.n_streams + kNsxWarpsPerCta - 1) / kNsxWarpsPerCta;
-  const size_t need = sizeof(uint32_t) * (kNsxCtaTableWords + kNsxWarpsPerCta * kNsxWarpWords);
-  const size_t smem = need;
-  nsx_process_kernel<ANA, NB><<<grid, kNsxWarpsPerCta * 32, smem, st>>>(p);
+  // CTA size: spread the batch over all SMs, as many lock-stepped warps per CTA as that allows
+  // (nsx_kernel.cuh, "CTA shape")
+  int dev = 0, sms = 0;
+  CU_OK(cudaGetDevice(&dev));
+  CU_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int w = (p.n_streams + sms - 1) / sms;
+  if (w < kNsxWarpsPerCta) w = kNsxWarpsPerCta;
+  if (w > kNsxMaxWarpsPerCta) w = kNsxMaxWarpsPerCta;
+  if (const char* e = getenv("NSB200_NSX_WARPS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kNsxMaxWarpsPerCta) w = v;
+  }
+  const int grid = (p.n_streams + w - 1) / w;
+  const size_t smem = sizeof(uint32_t) * (kNsxCtaTableWords + (size_t)w * kNsxWarpWords);
+  if (smem > 48 * 1024)   // per device and cheap: set on every large launch
+    CU_OK(cudaFuncSetAttribute(nsx_process_kernel<ANA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nsx_process_kernel<ANA, NB><<<grid, w * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
   return 0;

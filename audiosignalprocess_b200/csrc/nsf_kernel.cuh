@@ -31,7 +31,13 @@ namespace nsb200 {
 
 // 2-warp CTAs, 7 per SM (<= 146 registers): 14 resident streams per SM, so that the
 // headline 4096-stream batch is exactly two balanced rounds over 148 SMs.
-constexpr int kNsfWarpsPerCta = 2;
+#ifndef NSF_WARPS_PER_CTA
+#define NSF_WARPS_PER_CTA 2
+#endif
+#ifndef NSF_FRAME_SYNC
+#define NSF_FRAME_SYNC 0
+#endif
+constexpr int kNsfWarpsPerCta = NSF_WARPS_PER_CTA;
 #ifndef NSF_CTAS_PER_SM
 #define NSF_CTAS_PER_SM 8
 #endif
@@ -273,7 +279,11 @@ nsf_process_kernel(const NsfLaunch p) {
 
   if (p.frames > 0) load_frame(0, cur);
 
+  // optional lock step of the CTA's warps (full CTAs only): warps in the same phase share
+  // instruction-cache lines
+  const bool cta_sync = NSF_FRAME_SYNC && ((int)blockIdx.x + 1) * kNsfWarpsPerCta <= p.n_streams;
   for (int f = 0; f < p.frames; ++f) {
+    if (cta_sync) __syncthreads();
     float2 nxt[NB][kU] = {};
     if (f + 1 < p.frames) load_frame(f + 1, nxt);
 

@@ -26,11 +26,18 @@
 
 namespace nsb200 {
 
-constexpr int kNsxWarpsPerCta = 2;
-#ifndef NSX_CTAS_PER_SM
-#define NSX_CTAS_PER_SM 14
+// CTA shape: the loop body is ~7000 instructions (two fully unrolled 256-point int16 FFTs, ~30
+// inlined integer divisions), far more than the instruction cache holds once 28 warps per SM run
+// in 28 different places: "no instruction" was the dominant stall (profiles/r1_nsx_kernel_F100.md).
+// The warps of a CTA therefore meet at a barrier once per frame and walk the code together, and
+// the host picks the CTA size at launch (blockDim) so that a batch spreads over all SMs with
+// as many lock-stepped warps per CTA as possible: one 28-warp CTA per SM at 4096 streams
+// (measured 4.07 -> 2.99 ms per 4096 x 100 frames; more barriers per frame were slower).
+constexpr int kNsxWarpsPerCta = 2;        // smallest CTA (and the emulator's)
+constexpr int kNsxMaxWarpsPerCta = 28;    // 72 registers x 896 threads, 168 KB of shared memory
+#ifndef NSX_FRAME_SYNC
+#define NSX_FRAME_SYNC 1
 #endif
-constexpr int kNsxCtasPerSm = NSX_CTAS_PER_SM;
 constexpr int kNsxCtaTableWords = 128 + 128 + 128;   // window | twiddles | log2 fraction table
 constexpr int kNsxScratchWords = 256 + 136;          // FFT transposes | time / spectrum buffer
 constexpr int kNsxWarpWords = 2 * kNsxHdrWords + 2 * 129 * 4 + kNsxScratchWords;
@@ -183,7 +190,7 @@ NSB_DEV void nsx_extract_params(int* Hw, int* hist, int stages, int max_lrt, int
 }
 
 template <int ANA, int NB>
-__global__ void __launch_bounds__(kNsxWarpsPerCta * 32, kNsxCtasPerSm)
+__global__ void __launch_bounds__(kNsxMaxWarpsPerCta * 32, 1)
 nsx_process_kernel(const NsxLaunch p) {
   constexpr int LANES = ANA / 8;
   constexpr int HALF = ANA / 2;
@@ -199,13 +206,14 @@ nsx_process_kernel(const NsxLaunch p) {
   const int lane = lane_id();
   const int warp = (int)(threadIdx.x >> 5);
   const NsxTables* T = p.tables;
-  for (int i = (int)threadIdx.x; i < ANA; i += kNsxWarpsPerCta * 32)
+  const int warps_per_cta = (int)(blockDim.x >> 5);
+  for (int i = (int)threadIdx.x; i < ANA; i += (int)blockDim.x)
     s_win[i] = ANA == 256 ? T->win256[i] : T->win128[i];
-  for (int i = (int)threadIdx.x; i < 128; i += kNsxWarpsPerCta * 32) s_tw[i] = T->tw[i];
-  for (int i = (int)threadIdx.x; i < 256; i += kNsxWarpsPerCta * 32) s_logf[i] = T->log_frac[i];
+  for (int i = (int)threadIdx.x; i < 128; i += (int)blockDim.x) s_tw[i] = T->tw[i];
+  for (int i = (int)threadIdx.x; i < 256; i += (int)blockDim.x) s_logf[i] = T->log_frac[i];
   __syncthreads();
 
-  const int sidx = (int)blockIdx.x * kNsxWarpsPerCta + warp;
+  const int sidx = (int)blockIdx.x * warps_per_cta + warp;
   if (sidx >= p.n_streams) return;
 
   uint32_t* W = smem + kNsxCtaTableWords + warp * kNsxWarpWords;
@@ -266,7 +274,12 @@ nsx_process_kernel(const NsxLaunch p) {
   };
   if (p.frames > 0) load_frame(0, cur);
 
+  // optional lock step of the CTA's warps (full CTAs only): warps in the same phase share
+  // instruction-cache lines
+  const bool cta_sync = NSX_FRAME_SYNC && ((int)blockIdx.x + 1) * warps_per_cta <= p.n_streams;
+#define NSX_PHASE_SYNC() do { if (NSX_FRAME_SYNC >= 2 && cta_sync) __syncthreads(); } while (0)
   for (int f = 0; f < p.frames; ++f) {
+    if (cta_sync) __syncthreads();
     int nxt[NB][5] = {};
     if (f + 1 < p.frames) load_frame(f + 1, nxt);
     Hw[lane] = Hr[lane];
@@ -317,6 +330,8 @@ nsx_process_kernel(const NsxLaunch p) {
       for (int r = 0; r < 5; ++r) outv[r] = r < 3 ? syn_h[r] : 0;
 #pragma unroll
       for (int r = 0; r < 3; ++r) syn_h[r] = 0;
+      // as many barriers as the other branch (warps of one CTA may take different branches)
+      NSX_PHASE_SYNC(); NSX_PHASE_SYNC(); NSX_PHASE_SYNC(); NSX_PHASE_SYNC(); NSX_PHASE_SYNC();
     } else {
       const int block_index = Hr[kX_blockIndex] + 1;
       Hw[kX_blockIndex] = block_index;
@@ -490,6 +505,7 @@ nsx_process_kernel(const NsxLaunch p) {
         __syncwarp();
         state_ready = true;
       }
+      NSX_PHASE_SYNC();
       // ---- NoiseEstimation (nsx_core.c:334-452)
       unsigned noise[NSLOT];
       int q_noise = Hr[kX_qNoise];
@@ -672,6 +688,7 @@ nsx_process_kernel(const NsxLaunch p) {
         Hw[kX_timeAvgEnergy] = (int)time_avg;
       }
 
+      NSX_PHASE_SYNC();
       // ---- step 1: post / prior SNR (nsx_core.c:1723-1786)
       const unsigned sat_max = 1048575u;
       const int prev_q_magn = Hr[kX_prevQMagn], prev_q_noise = Hr[kX_prevQNoise];
@@ -821,6 +838,7 @@ nsx_process_kernel(const NsxLaunch p) {
         __syncwarp();
       }
 
+      NSX_PHASE_SYNC();
       // ---- WebRtcNsx_SpeechNoiseProb (nsx_core_c.c:26-261)
       unsigned nonspeech[NSLOT];
       int prior_ns;
@@ -1011,6 +1029,7 @@ nsx_process_kernel(const NsxLaunch p) {
       const int norm1 = fx_norm_u32(max_noise);
       const int q_noise_new = prev_q_noise + norm1 - 5;
 
+      NSX_PHASE_SYNC();
       // ---- step 3: Wiener filter (nsx_core.c:1949-2015), state save (:2019-2031)
       unsigned hb_psum = 0, hb_gsum = 0;
       {
@@ -1068,6 +1087,7 @@ nsx_process_kernel(const NsxLaunch p) {
       Hw[kX_prevQMagn] = q_magn;
       __syncwarp();
 
+      NSX_PHASE_SYNC();
       // ---- inverse FFT (real_fft.c:74-102): conjugate-symmetric extension,
       // bit reversal, radix-2 stages with data-dependent scaling
       {
