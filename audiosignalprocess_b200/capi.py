@@ -31,6 +31,11 @@ SYMBOLS = {
     "WebRtcNs_ProcessInterleavedF32": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_int]),
     "WebRtcNs_InitBatch": (C.c_int, [_HP, C.c_int, C.c_uint32, C.c_int]),
     "WebRtcNsx_InitBatch": (C.c_int, [_HP, C.c_int, C.c_uint32, C.c_int]),
+    "WebRtcNsB200_StateSize": (C.c_size_t, [_H]),
+    "WebRtcNsB200_ExportState": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
+    "WebRtcNsB200_ImportState": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
+    "WebRtcNsB200_MigrateHandle": (C.c_int, [_H, C.c_int]),
+    "WebRtcNsB200_HandleDevice": (C.c_int, [_H]),
     "WebRtcNsB200_SetCreateDevice": (C.c_int, [C.c_int]),
     "WebRtcNsB200_DeviceCount": (C.c_int, []),
     "WebRtcNsB200_Synchronize": (C.c_int, []),

@@ -1160,6 +1160,145 @@ int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_c
 
 using namespace nsb200;
 
+// ---- stream state snapshot / restore / migration ----------------------
+// A stream is its slabs (suppressor state, float histograms, band-split state) plus a few host
+// fields; the blob is those verbatim behind a small header, so restore is bit-exact.
+struct StateBlobHeader {
+  uint32_t tag;          // 'NSB2'
+  uint32_t magic;        // kMagicF / kMagicX
+  uint32_t fs;
+  int32_t mode;
+  int32_t init_flag;
+  int32_t analyze_seen;
+  double down_vsi;
+  uint32_t state_bytes, hist_bytes, band_bytes;
+  uint32_t reserved;
+  float analyze_frame[160];
+};
+constexpr uint32_t kBlobTag = 0x3242534eu;
+
+Handle* AnyHandle(const void* hv) {
+  Handle* h = static_cast<Handle*>(const_cast<void*>(hv));
+  return (h && (h->magic == kMagicF || h->magic == kMagicX)) ? h : nullptr;
+}
+struct SlabRefs { void* ptr[3]; size_t bytes[3]; };
+SlabRefs SlabsOf(DeviceCtx& d, const Handle* h, int slot) {
+  SlabRefs r = {};
+  SlabPool& sp = h->magic == kMagicF ? d.f_state : d.x_state;
+  r.ptr[0] = static_cast<char*>(sp.base) + (size_t)slot * sp.slab_bytes;
+  r.bytes[0] = sp.slab_bytes;
+  if (h->magic == kMagicF) {
+    r.ptr[1] = static_cast<char*>(d.f_hist.base) + (size_t)slot * d.f_hist.slab_bytes;
+    r.bytes[1] = d.f_hist.slab_bytes;
+  }
+  const int bslot = h->magic == kMagicF ? 2 * slot : 2 * slot + 1;
+  r.ptr[2] = static_cast<char*>(d.b_state.base) + (size_t)bslot * d.b_state.slab_bytes;
+  r.bytes[2] = d.b_state.slab_bytes;
+  return r;
+}
+size_t StateSize(const void* hv) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AnyHandle(hv);
+  if (!h) return 0;
+  SlabRefs r = SlabsOf(g_devs[h->dev], h, h->slot);
+  return sizeof(StateBlobHeader) + r.bytes[0] + r.bytes[1] + r.bytes[2];
+}
+int ExportState(const void* hv, void* buf, size_t size) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AnyHandle(hv);
+  if (!h) return Fail("bad handle");
+  if (!buf) return Fail("NULL buffer");
+  DeviceCtx* d;
+  if (DeviceReady(h->dev, &d) != 0) return -1;
+  SlabRefs r = SlabsOf(*d, h, h->slot);
+  const size_t need = sizeof(StateBlobHeader) + r.bytes[0] + r.bytes[1] + r.bytes[2];
+  if (size < need) return Fail("state buffer too small");
+  CU_OK(cudaDeviceSynchronize());   // everything enqueued for this stream has landed
+  StateBlobHeader hd = {};
+  hd.tag = kBlobTag;
+  hd.magic = h->magic;
+  hd.fs = h->fs;
+  hd.mode = h->mode;
+  hd.init_flag = h->init_flag;
+  hd.analyze_seen = h->analyze_seen ? 1 : 0;
+  hd.down_vsi = h->down_vsi;
+  hd.state_bytes = (uint32_t)r.bytes[0];
+  hd.hist_bytes = (uint32_t)r.bytes[1];
+  hd.band_bytes = (uint32_t)r.bytes[2];
+  memcpy(hd.analyze_frame, h->analyze_frame, sizeof(hd.analyze_frame));
+  char* p = static_cast<char*>(buf);
+  memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  for (int k = 0; k < 3; ++k) {
+    if (r.bytes[k]) CU_OK(cudaMemcpy(p, r.ptr[k], r.bytes[k], cudaMemcpyDeviceToHost));
+    p += r.bytes[k];
+  }
+  return 0;
+}
+int ImportState(void* hv, const void* buf, size_t size) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AnyHandle(hv);
+  if (!h) return Fail("bad handle");
+  if (!buf || size < sizeof(StateBlobHeader)) return Fail("state blob too small");
+  StateBlobHeader hd;
+  memcpy(&hd, buf, sizeof(hd));
+  if (hd.tag != kBlobTag) return Fail("not a state blob");
+  if (hd.magic != h->magic) return Fail("state blob is of the other suppressor kind (float / fixed)");
+  DeviceCtx* d;
+  if (DeviceReady(h->dev, &d) != 0) return -1;
+  SlabRefs r = SlabsOf(*d, h, h->slot);
+  if (hd.state_bytes != r.bytes[0] || hd.hist_bytes != r.bytes[1] || hd.band_bytes != r.bytes[2])
+    return Fail("state blob from an incompatible library version");
+  if (size < sizeof(hd) + r.bytes[0] + r.bytes[1] + r.bytes[2]) return Fail("state blob truncated");
+  CU_OK(cudaDeviceSynchronize());
+  const char* p = static_cast<const char*>(buf) + sizeof(hd);
+  for (int k = 0; k < 3; ++k) {
+    if (r.bytes[k]) CU_OK(cudaMemcpy(r.ptr[k], p, r.bytes[k], cudaMemcpyHostToDevice));
+    p += r.bytes[k];
+  }
+  h->fs = hd.fs;
+  h->mode = hd.mode;
+  h->init_flag = hd.init_flag;
+  h->analyze_seen = hd.analyze_seen != 0;
+  h->down_vsi = hd.down_vsi;
+  memcpy(h->analyze_frame, hd.analyze_frame, sizeof(h->analyze_frame));
+  return 0;
+}
+// Moves a stream to another GPU: new slot there, slabs copied device to device (NVLink peer copy
+// when the GPUs are peers, staged by the driver otherwise), old slot released.
+int MigrateHandle(void* hv, int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AnyHandle(hv);
+  if (!h) return Fail("bad handle");
+  if (EnsureDevices() != 0) return -1;
+  if (device < 0 || device >= (int)g_devs.size()) return Fail("bad device index");
+  if (device == h->dev) return 0;
+  DeviceCtx *src, *dst;
+  if (DeviceReady(h->dev, &src) != 0) return -1;
+  CU_OK(cudaDeviceSynchronize());
+  if (DeviceReady(device, &dst) != 0) return -1;
+  CU_OK(cudaDeviceSynchronize());
+  int slot = -1;
+  int rc;
+  if (h->magic == kMagicF) {
+    rc = PoolAlloc(*dst, dst->f_state, &slot);
+    if (rc == 0 && PoolGrow(*dst, dst->f_hist, dst->f_state.capacity) != 0) rc = -1;
+  } else {
+    rc = PoolAlloc(*dst, dst->x_state, &slot);
+  }
+  if (rc == 0 && PoolGrow(*dst, dst->b_state, 2 * (h->magic == kMagicF ? dst->f_state : dst->x_state).capacity) != 0) rc = -1;
+  if (rc != 0) return -1;
+  SlabRefs a = SlabsOf(*src, h, h->slot), b = SlabsOf(*dst, h, slot);
+  for (int k = 0; k < 3; ++k)
+    if (a.bytes[k]) CU_OK(cudaMemcpyPeer(b.ptr[k], device, a.ptr[k], h->dev, a.bytes[k]));
+  (h->magic == kMagicF ? src->f_state : src->x_state).free_slots.push_back(h->slot);
+  src->cached_slots.clear();
+  dst->cached_slots.clear();
+  h->dev = device;
+  h->slot = slot;
+  return 0;
+}
+
 extern "C" {
 
 int WebRtcNs_Create(NsHandle** h) { return Create(reinterpret_cast<void**>(h), kMagicF); }
@@ -1294,6 +1433,16 @@ int WebRtcNs_InitBatch(NsHandle* const* hs, int n, uint32_t fs, int mode) {
 }
 int WebRtcNsx_InitBatch(NsxHandle* const* hs, int n, uint32_t fs, int mode) {
   return InitMany(reinterpret_cast<void* const*>(hs), n, fs, mode, kMagicX);
+}
+
+size_t WebRtcNsB200_StateSize(const void* handle) { return StateSize(handle); }
+int WebRtcNsB200_ExportState(const void* handle, void* buf, size_t size) { return ExportState(handle, buf, size); }
+int WebRtcNsB200_ImportState(void* handle, const void* buf, size_t size) { return ImportState(handle, buf, size); }
+int WebRtcNsB200_MigrateHandle(void* handle, int device) { return MigrateHandle(handle, device); }
+int WebRtcNsB200_HandleDevice(const void* handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = AnyHandle(handle);
+  return h ? h->dev : -1;
 }
 
 int WebRtcNsB200_SetCreateDevice(int device) {

@@ -142,6 +142,19 @@ void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint3
 int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams,
                                 uint32_t n_samples, int64_t* sums, void* cuda_stream);
 
+/* ---- 5. stream state snapshot / restore / migration --------------------------- */
+/* No reference counterpart (the reference's state is a malloc'ed struct the caller could memcpy:
+ * NoiseSuppressionC, ns_core.h:52-114; NoiseSuppressionFixedC, nsx_core.h:22-110); here the state
+ * lives in GPU slabs, so long-lived streams get explicit calls.  `handle` is an NsHandle* or an
+ * NsxHandle*.  Export waits for the stream's enqueued work; Import restores bit-exactly into any
+ * handle of the same kind (on any GPU), after which processing continues as if uninterrupted.
+ * Migrate moves the stream's slabs to another GPU (peer copy) and keeps the handle valid. */
+size_t WebRtcNsB200_StateSize(const void* handle);              /* bytes; 0 on a bad handle */
+int WebRtcNsB200_ExportState(const void* handle, void* buf, size_t size);
+int WebRtcNsB200_ImportState(void* handle, const void* buf, size_t size);
+int WebRtcNsB200_MigrateHandle(void* handle, int device);
+int WebRtcNsB200_HandleDevice(const void* handle);              /* -1 on a bad handle */
+
 #ifdef __cplusplus
 }
 #endif
