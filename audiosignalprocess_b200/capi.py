@@ -27,6 +27,9 @@ SYMBOLS = {
     "WebRtcNs_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNsx_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNs_ProcessBatchBandsF32": (C.c_int, [_HP, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "WebRtcNs_AnalyzeProcessBatch": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "WebRtcNs_AnalyzeProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "WebRtcNs_AnalyzeProcessBatchBandsF32": (C.c_int, [_HP, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "WebRtcNs_ProcessInterleavedI16": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_int]),
     "WebRtcNs_ProcessInterleavedF32": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_int]),
     "WebRtcNs_InitBatch": (C.c_int, [_HP, C.c_int, C.c_uint32, C.c_int]),

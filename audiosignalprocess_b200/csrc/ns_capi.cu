@@ -56,6 +56,7 @@ struct Handle {
   int init_flag;
   bool analyze_seen;
   float analyze_frame[160];
+  bool split_mode;   // float NS: the stream has been fed distinct Analyze / Process signals (sticky)
   double down_vsi;   // 48 kHz: running position of the 640 -> 480 resampler (band_host_init.h)
 };
 
@@ -261,6 +262,7 @@ int Create(void** out, uint32_t magic) {
   h->fs = 0;
   h->mode = 0;
   h->analyze_seen = false;
+  h->split_mode = false;
   int rc;
   if (magic == kMagicF) {
     rc = PoolAlloc(*d, d->f_state, &h->slot);
@@ -412,24 +414,39 @@ int SetPolicy(void* hv, int mode, uint32_t magic) {
 // kernel is fastest at 8 two-warp CTAs per SM (128 registers, no spills that matter) and the
 // fixed-point kernel at 14 (72 registers); padding shared memory to force "balanced" full waves
 // (7 CTAs/SM = exactly two rounds for 4096 streams) was slower than the fuller occupancy.
-template <int ANA, int NB, bool I16>
+template <int ANA, int NB, bool I16, bool SPLIT>
 int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
-  const size_t need = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords);
-  const size_t smem = need;
+  const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * (SPLIT ? kNsfWarpWordsSplit : kNsfWarpWords));
   if (smem > 48 * 1024)
-    CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nsf_process_kernel<ANA, NB, I16><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
+    CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nsf_process_kernel<ANA, NB, I16, SPLIT><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
   ++g_launches;
   CU_OK(cudaGetLastError());
   return 0;
 }
-int LaunchNsf(int ana, int nb, bool i16, const NsfLaunch& p, cudaStream_t st) {
-  if (ana == 128 && nb == 1) return i16 ? LaunchNsfT<128, 1, true>(p, st) : LaunchNsfT<128, 1, false>(p, st);
-  if (ana == 256 && nb == 1) return i16 ? LaunchNsfT<256, 1, true>(p, st) : LaunchNsfT<256, 1, false>(p, st);
-  if (ana == 256 && nb == 2) return i16 ? LaunchNsfT<256, 2, true>(p, st) : LaunchNsfT<256, 2, false>(p, st);
-  if (ana == 256 && nb == 3) return i16 ? LaunchNsfT<256, 3, true>(p, st) : LaunchNsfT<256, 3, false>(p, st);
+template <int ANA, int NB>
+int LaunchNsfV(bool i16, bool split, const NsfLaunch& p, cudaStream_t st) {
+  if (split) return i16 ? LaunchNsfT<ANA, NB, true, true>(p, st) : LaunchNsfT<ANA, NB, false, true>(p, st);
+  return i16 ? LaunchNsfT<ANA, NB, true, false>(p, st) : LaunchNsfT<ANA, NB, false, false>(p, st);
+}
+// split: Analyze is fed p.ana_in, Process p.in (nsf_kernel.cuh, SPLIT)
+int LaunchNsf(int ana, int nb, bool i16, bool split, const NsfLaunch& p, cudaStream_t st) {
+  if (ana == 128 && nb == 1) return LaunchNsfV<128, 1>(i16, split, p, st);
+  if (ana == 256 && nb == 1) return LaunchNsfV<256, 1>(i16, split, p, st);
+  if (ana == 256 && nb == 2) return LaunchNsfV<256, 2>(i16, split, p, st);
+  if (ana == 256 && nb == 3) return LaunchNsfV<256, 3>(i16, split, p, st);
   return Fail("unsupported (fs, num_bands) combination");
+}
+// Split mode is sticky: once a stream has seen distinct Analyze / Process signals its two
+// histories and magnitude memories differ, so later fused calls on it run the split kernel with
+// the Process signal fed to both (identical results to the reference either way).
+bool NeedSplit(std::vector<Handle*>& hs, bool split_call) {
+  bool split = split_call;
+  for (Handle* h : hs) split = split || h->split_mode;
+  if (split)
+    for (Handle* h : hs) h->split_mode = true;
+  return split;
 }
 
 template <int ANA, int NB>
@@ -479,7 +496,8 @@ constexpr int kBandBlockFrames = 100;    // frames per pipelined block (bounds t
 
 // NS launch over the whole batch, frames [f0, f0 + nf) of PCM laid out with the given strides.
 int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t* in, long long in_ss,
-             int16_t* out, long long out_ss, long long fstride, long long bstride, int f0, int nf, cudaStream_t s) {
+             int16_t* out, long long out_ss, long long fstride, long long bstride, int f0, int nf, cudaStream_t s,
+             bool split = false, const int16_t* ana_in = nullptr, long long ana_ss = 0, long long ana_fs = 0) {
   if (magic == kMagicF) {
     NsfLaunch p;
     p.state = (float*)d.f_state.base;
@@ -494,7 +512,11 @@ int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t
     p.in_band_stride = p.out_band_stride = bstride;
     p.n_streams = n;
     p.frames = nf;
-    return LaunchNsf(ana, nb, true, p, s);
+    // split without a separate Analyze signal (sticky split mode): band 0 of the input serves both
+    p.ana_in = ana_in ? ana_in + (size_t)f0 * ana_fs : in + (size_t)f0 * fstride;
+    p.ana_stream_stride = ana_in ? ana_ss : in_ss;
+    p.ana_frame_stride = ana_in ? ana_fs : fstride;
+    return LaunchNsf(ana, nb, true, split, p, s);
   }
   NsxLaunch p;
   p.state = (uint32_t*)d.x_state.base;
@@ -521,7 +543,7 @@ int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t
 // (stream order), and the stages of neighbouring chunks overlap on the otherwise idle SMs.
 // With `host`, the H2D and D2H copies are two more stages of the same pipeline.
 int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in, size_t in_stride,
-                 int16_t* d_out, size_t out_stride, int frames, cudaStream_t st, const HostIo* host) {
+                 int16_t* d_out, size_t out_stride, int frames, cudaStream_t st, const HostIo* host, bool split) {
   const int n = (int)hs.size();
   const uint32_t fs = hs[0]->fs;
   const int nb = NumBands(fs);
@@ -672,7 +694,7 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
                                 d_out + (size_t)f0 * fl, out_stride * sizeof(int16_t),
                                 (size_t)nf * fl * sizeof(int16_t), n, cudaMemcpyDeviceToHost, s));
       } else if (bk == ns_stage) {
-        if (LaunchNs(d, magic, ana, nb, n, d.d_bands, bands_ss, d.d_bands, bands_ss, nb * 160, 160, f0, nf, s) != 0)
+        if (LaunchNs(d, magic, ana, nb, n, d.d_bands, bands_ss, d.d_bands, bands_ss, nb * 160, 160, f0, nf, s, split) != 0)
           return -1;
       } else {
         if (LaunchBandStage(nb, bl, bk, f0, nf, s, &g_launches) != 0) return Fail("band stage launch failed");
@@ -702,9 +724,10 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
 // Enqueues the suppressor (with band split / merge at 32/48 kHz) for the streams of one device.
 // d_in / d_out: full-band int16 PCM in device memory; with `host` (32/48 kHz only) they are
 // staging buffers the pipeline fills from / drains to the host buffers itself.
+// d_ana (float NS at 8/16 kHz only): separate signal for Analyze, [stream][frame][fs/100] int16.
 int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int16_t* d_in,
               size_t in_stride, int16_t* d_out, size_t out_stride, int frames, cudaStream_t st,
-              const HostIo* host = nullptr) {
+              const HostIo* host = nullptr, const int16_t* d_ana = nullptr, size_t ana_stride = 0) {
   const int n = (int)hs.size();
   const uint32_t fs = hs[0]->fs;
   const int nb = NumBands(fs);
@@ -716,9 +739,13 @@ int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int1
     if (nb > 1) all[n + i] = BandSlot(hs[i]);
   }
   if (UploadSlots(d, all, st) != 0) return -1;
+  if (d_ana && (magic != kMagicF || nb != 1))
+    return Fail("a separate Analyze signal is supported for the float suppressor on full-band PCM at 8/16 kHz "
+                "(use WebRtcNs_AnalyzeProcessBatchBandsF32 on band frames at 32/48 kHz)");
+  const bool split = magic == kMagicF && NeedSplit(hs, d_ana != nullptr);
   if (nb == 1)
     return LaunchNs(d, magic, fs == 8000 ? 128 : 256, 1, n, d_in, (long long)in_stride, d_out, (long long)out_stride,
-                    fl, 0, 0, frames, st);
+                    fl, 0, 0, frames, st, split, d_ana, (long long)ana_stride, fl);
   if ((in_stride | out_stride) & 7) return Fail("strides must be multiples of 8 samples at 32/48 kHz");
   for (int f0 = 0; f0 < frames; f0 += kBandBlockFrames) {
     const int nf = frames - f0 < kBandBlockFrames ? frames - f0 : kBandBlockFrames;
@@ -729,7 +756,7 @@ int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int1
       h.out += (size_t)f0 * fl;
     }
     if (RunBandBlock(d, magic, hs, d_in + (size_t)f0 * fl, in_stride, d_out + (size_t)f0 * fl, out_stride, nf, st,
-                     host ? &h : nullptr) != 0)
+                     host ? &h : nullptr, split) != 0)
       return -1;
   }
   return 0;
@@ -939,8 +966,9 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
 }
 
 // Single-stream float call = batch of one over float band frames.
+// ana (optional): [stream][frame][frame_len] band-0 frames for Analyze, stride ana_ss floats.
 int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_ss, float* out,
-                    size_t out_ss, int frames) {
+                    size_t out_ss, int frames, const float* ana = nullptr, size_t ana_ss = 0) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!hv || n <= 0) return Fail("no handles");
   if (nb < 1 || nb > 3) return Fail("num_bands out of range");
@@ -957,13 +985,15 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
   const uint32_t fs = hs[0]->fs;
   if (fs == 8000 && nb != 1) return Fail("8 kHz has a single band");
   const int fl = fs == 8000 ? 80 : 160;
-  const int ana = fs == 8000 ? 128 : 256;
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
-  const size_t per = (size_t)frames * nb * fl;
-  float *din = nullptr, *dout = nullptr;
+  const size_t per = (size_t)frames * nb * fl, per_a = (size_t)frames * fl;
+  if (n > 1 && (in_ss < per || out_ss < per || (ana && ana_ss < per_a))) return Fail("stride shorter than the frames of one stream");
+  const bool split = NeedSplit(hs, ana != nullptr);
+  float *din = nullptr, *dout = nullptr, *dana = nullptr;
   CU_OK(cudaMalloc(&din, sizeof(float) * per * n));
   CU_OK(cudaMalloc(&dout, sizeof(float) * per * n));
+  if (ana) CU_OK(cudaMalloc(&dana, sizeof(float) * per_a * n));
   int rc = 0;
   do {
     std::vector<int> slots(n);
@@ -972,6 +1002,11 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
     cudaError_t e = cudaMemcpy2DAsync(din, per * sizeof(float), in, in_ss * sizeof(float), per * sizeof(float), n,
                                       cudaMemcpyHostToDevice, d->stream);
     if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    if (ana) {
+      e = cudaMemcpy2DAsync(dana, per_a * sizeof(float), ana, ana_ss * sizeof(float), per_a * sizeof(float), n,
+                            cudaMemcpyHostToDevice, d->stream);
+      if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    }
     NsfLaunch p;
     p.state = (float*)d->f_state.base;
     p.hist = (int*)d->f_hist.base;
@@ -984,7 +1019,10 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
     p.in_band_stride = p.out_band_stride = fl;
     p.n_streams = n;
     p.frames = frames;
-    if ((rc = LaunchNsf(ana, nb, false, p, d->stream)) != 0) break;
+    p.ana_in = ana ? dana : din;
+    p.ana_stream_stride = ana ? (long long)per_a : (long long)per;
+    p.ana_frame_stride = ana ? (long long)fl : (long long)nb * fl;
+    if ((rc = LaunchNsf(fs == 8000 ? 128 : 256, nb, false, split, p, d->stream)) != 0) break;
     e = cudaMemcpy2DAsync(out, out_ss * sizeof(float), dout, per * sizeof(float), per * sizeof(float), n,
                           cudaMemcpyDeviceToHost, d->stream);
     if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
@@ -993,7 +1031,56 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
   } while (0);
   cudaFree(din);
   cudaFree(dout);
+  if (dana) cudaFree(dana);
   return rc;
+}
+
+// Full-band int16 PCM with a separate Analyze signal, host pointers (8/16 kHz, float NS).
+int SplitBatchHost(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
+                   int16_t* out, size_t out_stride, int frames) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<Handle*> hs;
+  if (!ana) return Fail("NULL Analyze signal");
+  if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (frames == 0) return 0;
+  const int fl = (int)hs[0]->fs / 100;
+  const size_t per = (size_t)frames * fl;
+  if ((ana_stride & 1) || (n > 1 && ana_stride < per)) return Fail("bad Analyze stride");
+  for (int i = 1; i < n; ++i)
+    if (hs[i]->dev != hs[0]->dev) return Fail("split batch spans several GPUs");
+  DeviceCtx* d;
+  if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
+  int16_t* buf = nullptr;
+  CU_OK(cudaMalloc(&buf, sizeof(int16_t) * per * n * 3));
+  int16_t *dana = buf, *din = buf + per * n, *dout = buf + 2 * per * n;
+  int rc = 0;
+  do {
+    cudaError_t e = cudaMemcpy2DAsync(dana, per * 2, ana, ana_stride * 2, per * 2, n, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(din, per * 2, in, in_stride * 2, per * 2, n, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+    if ((rc = RunDevice(*d, kMagicF, hs, din, per, dout, per, frames, d->stream, nullptr, dana, per)) != 0) break;
+    e = cudaMemcpy2DAsync(out, out_stride * 2, dout, per * 2, per * 2, n, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
+  } while (0);
+  cudaFree(buf);
+  return rc;
+}
+int SplitBatchDevice(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
+                     int16_t* out, size_t out_stride, int frames, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<Handle*> hs;
+  if (!ana) return Fail("NULL Analyze signal");
+  if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (frames == 0) return 0;
+  if ((ana_stride & 1) || (n > 1 && ana_stride < (size_t)frames * (hs[0]->fs / 100))) return Fail("bad Analyze stride");
+  for (int i = 1; i < n; ++i)
+    if (hs[i]->dev != hs[0]->dev) return Fail("device batch spans several GPUs");
+  DeviceCtx* d;
+  if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
+  cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+  return RunDevice(*d, kMagicF, hs, in, in_stride, out, out_stride, frames, st, nullptr, ana, ana_stride);
 }
 
 // ---- interleaved multi-channel front end (APM_NS::processCaptureStream, libapm/src/apm_ns.cpp:47-132)
@@ -1170,6 +1257,8 @@ struct StateBlobHeader {
   int32_t mode;
   int32_t init_flag;
   int32_t analyze_seen;
+  int32_t split_mode;
+  int32_t pad0;
   double down_vsi;
   uint32_t state_bytes, hist_bytes, band_bytes;
   uint32_t reserved;
@@ -1221,6 +1310,7 @@ int ExportState(const void* hv, void* buf, size_t size) {
   hd.mode = h->mode;
   hd.init_flag = h->init_flag;
   hd.analyze_seen = h->analyze_seen ? 1 : 0;
+  hd.split_mode = h->split_mode ? 1 : 0;
   hd.down_vsi = h->down_vsi;
   hd.state_bytes = (uint32_t)r.bytes[0];
   hd.hist_bytes = (uint32_t)r.bytes[1];
@@ -1260,6 +1350,7 @@ int ImportState(void* hv, const void* buf, size_t size) {
   h->mode = hd.mode;
   h->init_flag = hd.init_flag;
   h->analyze_seen = hd.analyze_seen != 0;
+  h->split_mode = hd.split_mode != 0;
   h->down_vsi = hd.down_vsi;
   memcpy(h->analyze_frame, hd.analyze_frame, sizeof(h->analyze_frame));
   return 0;
@@ -1330,14 +1421,15 @@ void WebRtcNs_Process(NsHandle* hv, const float* const* spframe, int num_bands, 
   const int fl = h->fs == 8000 ? 80 : 160;
   float in[3 * 160], out[3 * 160];
   for (int b = 0; b < num_bands; ++b) memcpy(in + b * fl, spframe[b], sizeof(float) * fl);
-  if (h->analyze_seen && memcmp(h->analyze_frame, in, sizeof(float) * fl) != 0) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_err = "WebRtcNs_Process: band 0 differs from the frame given to WebRtcNs_Analyze; "
-            "statistics are taken from the Process frame (fused path)";
-  }
+  // Analyze recorded its frame; a different band-0 frame here (an echo canceller in between)
+  // takes the split kernel.  Process without a preceding Analyze is fed to both, as every
+  // caller in the reference tree does.
+  const bool distinct = h->analyze_seen && memcmp(h->analyze_frame, in, sizeof(float) * fl) != 0;
   h->analyze_seen = false;
   void* one = h;
-  if (ProcessBandsF32(&one, 1, num_bands, in, (size_t)num_bands * fl, out, (size_t)num_bands * fl, 1) != 0) return;
+  if (ProcessBandsF32(&one, 1, num_bands, in, (size_t)num_bands * fl, out, (size_t)num_bands * fl, 1,
+                      distinct ? h->analyze_frame : nullptr, (size_t)fl) != 0)
+    return;
   for (int b = 0; b < num_bands; ++b) memcpy(outframe[b], out + b * fl, sizeof(float) * fl);
 }
 
@@ -1421,6 +1513,22 @@ int WebRtcNsx_ProcessBatchDevice(NsxHandle* const* hs, int n, const int16_t* in,
 int WebRtcNs_ProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* in, size_t is, float* out,
                                   size_t os, int frames) {
   return ProcessBandsF32(reinterpret_cast<void* const*>(hs), n, nb, in, is, out, os, frames);
+}
+int WebRtcNs_AnalyzeProcessBatch(NsHandle* const* hs, int n, const int16_t* ana, size_t as, const int16_t* in, size_t is,
+                                 int16_t* out, size_t os, int frames) {
+  return SplitBatchHost((void* const*)hs, n, ana, as, in, is, out, os, frames);
+}
+int WebRtcNs_AnalyzeProcessBatchDevice(NsHandle* const* hs, int n, const int16_t* ana, size_t as, const int16_t* in,
+                                       size_t is, int16_t* out, size_t os, int frames, void* stream) {
+  return SplitBatchDevice((void* const*)hs, n, ana, as, in, is, out, os, frames, stream);
+}
+int WebRtcNs_AnalyzeProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* ana, size_t as, const float* in,
+                                         size_t is, float* out, size_t os, int frames) {
+  if (!ana) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return Fail("NULL Analyze signal");
+  }
+  return ProcessBandsF32((void* const*)hs, n, nb, in, is, out, os, frames, ana, as);
 }
 int WebRtcNs_ProcessInterleavedI16(NsHandle* const* hs, int n_channels, int16_t* data, int samples_per_channel) {
   return ProcessInterleaved<int16_t>(reinterpret_cast<void* const*>(hs), n_channels, data, samples_per_channel);

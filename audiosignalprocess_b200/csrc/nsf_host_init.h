@@ -89,6 +89,7 @@ inline void nsf_init_state(uint32_t* slab, uint32_t fs) {
     i[kH_counter + s] = (int)floor((float)(200 * (s + 1)) / 3.f);  // 66, 133, 200
   i[kH_modelUpd0] = 2;
   i[kH_modelUpd3] = 500;
+  i[kH_splitValid] = 1;   // all-zero split arrays are what InitCore leaves (ns_core.c:103-131)
   const float pars[7] = {0.5f, 0.5f, 1.f, 0.5f, 1.f, 0.f, 0.f};
   for (int k = 0; k < 7; ++k) f[kH_priorPars + k] = pars[k];
   f[kH_priorSpeechProb] = 0.5f;

@@ -42,8 +42,9 @@ constexpr int kNsfWarpsPerCta = NSF_WARPS_PER_CTA;
 #define NSF_CTAS_PER_SM 8
 #endif
 constexpr int kNsfCtasPerSm = NSF_CTAS_PER_SM;
-constexpr int kNsfCtaTableWords = 912;  // win 256 | tw 512 | logi 132 | pad
+constexpr int kNsfCtaTableWords = 912 + 2 * kFftTw12F2;  // win 256 | tw 512 | logi 132 | pad | regrouped twiddles 240
 constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
+constexpr int kNsfWarpWordsSplit = kNsfWarpWords + 4 * kNsfAuxStride;   // + noise | speechProb | parametric | magnPrevProcess
 
 template <int ANA>
 struct NsfGeo {
@@ -172,7 +173,12 @@ NSB_DEV void nsf_extract_params(float* H, int* hist, int lane) {
 // ANA: 256 (16/32/48 kHz band 0) or 128 (8 kHz). NB: number of bands (1..3).
 // I16: PCM is int16 (rounded on output like IFChannelBuffer::RefreshI,
 // channel_buffer.cc:55-60) or float in int16 scale (the WebRtcNs_Process ABI).
-template <int ANA, int NB, bool I16>
+// SPLIT: Analyze and Process are fed different band-0 signals (p.ana_in / p.in), as when an
+// echo canceller sits between them (audio_processing_impl.cc:625-631).  The analysis keeps its
+// own history, the process side gets its own forward FFT, and what one frame implies in the
+// fused case -- noise == noisePrev, magnPrevAnalyze == magnPrevProcess, speechProb and
+// parametricNoise living in registers -- becomes four extra per-bin arrays (nsf_layout.h).
+template <int ANA, int NB, bool I16, bool SPLIT>
 __global__ void __launch_bounds__(kNsfWarpsPerCta * 32, kNsfCtasPerSm)
 nsf_process_kernel(const NsfLaunch p) {
   typedef NsfGeo<ANA> G;
@@ -189,12 +195,15 @@ nsf_process_kernel(const NsfLaunch p) {
     s_win[i] = ANA == 256 ? T->win256[i] : T->win128[i];
   for (int i = (int)threadIdx.x; i < 256; i += kNsfWarpsPerCta * 32) s_tw[i] = T->tw[i];
   for (int i = (int)threadIdx.x; i < 132; i += kNsfWarpsPerCta * 32) s_logi[i] = T->logi[i];
+  float2* s_tw12 = reinterpret_cast<float2*>(smem + 912);
+  __syncthreads();
+  fft_fill_tw12<G::kNC>(s_tw12, s_tw, (int)threadIdx.x, kNsfWarpsPerCta * 32);
   __syncthreads();
 
   const int sidx = (int)blockIdx.x * kNsfWarpsPerCta + warp;
   if (sidx >= p.n_streams) return;  // whole warp leaves; no block barriers below
 
-  float* W = smem + kNsfCtaTableWords + warp * kNsfWarpWords;
+  float* W = smem + kNsfCtaTableWords + warp * (SPLIT ? kNsfWarpWordsSplit : kNsfWarpWords);
   // Header scalars are double buffered: within a frame every lane reads the
   // frame-start copy (Hr) and writes the next copy (Hw) with warp-uniform
   // values, so there is never a read-modify-write race between lanes.
@@ -202,6 +211,10 @@ nsf_process_kernel(const NsfLaunch p) {
   float* Hw = W + kNsfHdrWords;
   float* B = W + 2 * kNsfHdrWords;            // per-bin records
   float2* scr = reinterpret_cast<float2*>(B + 129 * kNsfBinRec);  // FFT scratch (8-byte aligned)
+  float* X_noise = B + 129 * kNsfBinRec + 2 * kFftScratchF2;       // split mode: self->noise
+  float* X_prob = X_noise + kNsfAuxStride;                          //   self->speechProb
+  float* X_param = X_prob + kNsfAuxStride;                          //   self->parametricNoise
+  float* X_magnP = X_param + kNsfAuxStride;                         //   self->magnPrevProcess
 
   const int slot = p.slots[sidx];
   float* gS = p.state + (size_t)slot * kNsfStateWords;
@@ -215,9 +228,15 @@ nsf_process_kernel(const NsfLaunch p) {
     const float4* src = reinterpret_cast<const float4*>(gS + kNsfOffBins);
     float4* dst = reinterpret_cast<float4*>(B);
     for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) async_copy16(dst + i, src + i);
+    if (SPLIT) {
+      const float4* xs = reinterpret_cast<const float4*>(gS + kNsfOffAux);
+      float4* xd = reinterpret_cast<float4*>(X_noise);
+      for (int i = lane; i < 4 * kNsfAuxStride / 4; i += 32) async_copy16(xd + i, xs + i);
+    }
   }
   bool state_ready = false;
   float2 hx[2], sy[2];       // analysis history / synthesis overlap, pair p = lane + 32u
+  float2 hp[2];              // split mode: history of the Process signal (dataBuf)
   float2 hb[NB > 1 ? NB - 1 : 1][2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -227,6 +246,8 @@ nsf_process_kernel(const NsfLaunch p) {
       hx[u] = reinterpret_cast<const float2*>(gS + kNsfOffXHist)[pr];
       sy[u] = reinterpret_cast<const float2*>(gS + kNsfOffSynt)[pr];
     }
+    hp[u] = make_float2(0.f, 0.f);
+    if (SPLIT && pr < G::kHP) hp[u] = reinterpret_cast<const float2*>(gS + kNsfOffPHist)[pr];
 #pragma unroll
     for (int b = 0; b < NB - 1; ++b) {
       hb[b][u] = make_float2(0.f, 0.f);
@@ -234,6 +255,24 @@ nsf_process_kernel(const NsfLaunch p) {
     }
   }
   __syncwarp();
+  if (SPLIT) {
+    async_copy_wait_all();
+    __syncwarp();
+    state_ready = true;
+    if (reinterpret_cast<const int*>(Hr)[kH_splitValid] == 0) {
+      // the stream was driven by the fused kernel so far: one frame for both sides means
+      // noise == noisePrev, magnPrevProcess == magnPrevAnalyze, dataBuf == analyzeBuf
+      for (int k = lane; k < G::kBins; k += 32) {
+        X_noise[k] = B[k * kNsfBinRec + kB_noisePrev];
+        X_magnP[k] = B[k * kNsfBinRec + kB_magnPrev];
+        X_prob[k] = 0.f;
+        X_param[k] = 0.f;
+      }
+      hp[0] = hx[0];
+      hp[1] = hx[1];
+      __syncwarp();
+    }
+  }
 
   const float overdrive = Hr[kH_overdrive];
   const float denoiseBound = Hr[kH_denoiseBound];
@@ -277,7 +316,26 @@ nsf_process_kernel(const NsfLaunch p) {
     }
   };
 
+  // split mode: band-0 frame of the Analyze signal
+  float2 curA[kU];
+  auto load_ana = [&](int f, float2 (&dst)[kU]) {
+    const size_t off = (size_t)sidx * (size_t)p.ana_stream_stride + (size_t)f * (size_t)p.ana_frame_stride;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int w = lane + 32 * u;
+      dst[u] = make_float2(0.f, 0.f);
+      if (w < G::kFP) {
+        if (I16) {
+          const uint32_t v = reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.ana_in) + off)[w];
+          dst[u] = make_float2((float)(int16_t)(v & 0xffffu), (float)(int16_t)(v >> 16));
+        } else {
+          dst[u] = reinterpret_cast<const float2*>(static_cast<const float*>(p.ana_in) + off)[w];
+        }
+      }
+    }
+  };
   if (p.frames > 0) load_frame(0, cur);
+  if (SPLIT && p.frames > 0) load_ana(0, curA);
 
   // optional lock step of the CTA's warps (full CTAs only): warps in the same phase share
   // instruction-cache lines
@@ -285,7 +343,9 @@ nsf_process_kernel(const NsfLaunch p) {
   for (int f = 0; f < p.frames; ++f) {
     if (cta_sync) __syncthreads();
     float2 nxt[NB][kU] = {};
+    float2 nxtA[kU] = {};
     if (f + 1 < p.frames) load_frame(f + 1, nxt);
+    if (SPLIT && f + 1 < p.frames) load_ana(f + 1, nxtA);
 
     const int* HIr = reinterpret_cast<const int*>(Hr);
     int* HIw = reinterpret_cast<int*>(Hw);
@@ -298,7 +358,7 @@ nsf_process_kernel(const NsfLaunch p) {
       if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hx[u];
 #pragma unroll
     for (int u = 0; u < kU; ++u)
-      if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[0][u];
+      if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = SPLIT ? curA[u] : cur[0][u];
     __syncwarp();
     float2 v[4];
 #pragma unroll
@@ -325,29 +385,30 @@ nsf_process_kernel(const NsfLaunch p) {
     float hbGain = 1.f;
     bool hbApplyGain = false;
 
-    if (energy1 == 0.f) {
-      // ---- zero input (ns_core.c:1072-1082, 1239-1264): no statistics update,
-      // flush the overlap, high bands pass through the delay line ungained.
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int pr = lane + 32 * u;
-        o0[u] = (u < 2 && pr < G::kHP) ? sy[u < 2 ? u : 0] : make_float2(0.f, 0.f);
-      }
-      sy[0] = sy[1] = make_float2(0.f, 0.f);
-    } else {
-      const int blockInd = HIr[kH_blockInd] + 1;
+    // values handed from the analysis to the process part (fused: in registers; split: the
+    // process part reloads them from the state it shares with Analyze)
+    int blockInd = HIr[kH_blockInd];
+    float re[G::kSlots], im[G::kSlots], magn[G::kSlots];
+    float noise[G::kSlots], prevEst[G::kSlots], parametric[G::kSlots], prob[G::kSlots];
+    float noisePrev[G::kSlots], logLrt[G::kSlots], mpause[G::kSlots];
+    float prior = 0.f;
+    const float energyA = energy1;   // energy of the analysed frame (ns_core.c:1071)
+
+    if (energyA != 0.f) {
+      // ======== WebRtcNs_AnalyzeCore (zero input: no statistics update, ns_core.c:1072-1082)
+      blockInd = HIr[kH_blockInd] + 1;
       HIw[kH_blockInd] = blockInd;
       const int updateParsFlag = HIr[kH_modelUpd0];
 
       // ---- (c) forward FFT (ns_core.c:886-911)
-      warp_fft<G::kNC, +1>(v, scr, s_tw, lane);
+      warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
       if (lane < G::kL) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
       }
       __syncwarp();
 
-      float re[G::kSlots], im[G::kSlots], magn[G::kSlots], lmagn[G::kSlots];
+      float lmagn[G::kSlots];
       float sigE = 0.f, sumMagn = 0.f;
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
@@ -396,7 +457,7 @@ nsf_process_kernel(const NsfLaunch p) {
         rc1[s] = frcp_nr(c1[s]);
         cf[s] = (float)cnt[s];
       }
-      float noise[G::kSlots], smoothPrev[G::kSlots];
+      float smoothPrev[G::kSlots];
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
@@ -428,7 +489,6 @@ nsf_process_kernel(const NsfLaunch p) {
       }
 
       // ---- (e) start-up: white / pink parametric noise (ns_core.c:1088-1162)
-      float parametric[G::kSlots];
       if (blockInd < 50) {
         float slm = 0.f, slilm = 0.f;
 #pragma unroll
@@ -491,8 +551,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
 
       // ---- (g) ComputeSnr (ns_core.c:566-588) + feature sums
-      float prevEst[G::kSlots], snrPrior[G::kSlots], snrPost[G::kSlots];
-      float mpause[G::kSlots], noisePrev[G::kSlots], logLrt[G::kSlots];
+      float snrPrior[G::kSlots], snrPost[G::kSlots];
       float sumPause = 0.f, sumLog = 0.f;
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
@@ -516,7 +575,7 @@ nsf_process_kernel(const NsfLaunch p) {
       warp_sum2(sumPause, sumLog);
 
       // ---- (h) FeatureUpdate (ns_core.c:755-791)
-      float feat0, feat4, prior;
+      float feat0, feat4;
       {
         // spectral flatness (:523-556); magn >= 1 so the log(0) exit is dead
         float den = sumMagn - __shfl_sync(kFullMask, magn[0], 0);
@@ -582,7 +641,6 @@ nsf_process_kernel(const NsfLaunch p) {
       }
 
       // ---- (i) SpeechNoiseProb (ns_core.c:642-749)
-      float prob[G::kSlots];
       {
         float lsum = 0.f;
 #pragma unroll
@@ -654,9 +712,97 @@ nsf_process_kernel(const NsfLaunch p) {
         }
         noise[j] = nz;
       }
+      if (SPLIT) {
+        // ns_core.c:1178-1180 and the fields Process reads later: noise, magnPrevAnalyze,
+        // speechProb, parametricNoise; noisePrev stays as the last Process left it
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
+          if (!nyq || lane == 0) {
+            *reinterpret_cast<float4*>(B + k * kNsfBinRec + 8) = make_float4(noisePrev[j], magn[j], logLrt[j], mpause[j]);
+            X_noise[k] = noise[j];
+            X_prob[k] = prob[j];
+            if (blockInd < 50) X_param[k] = parametric[j];
+          }
+        }
+        __syncwarp();
+      }
+    }
 
+    if (SPLIT) {
+      // ======== WebRtcNs_ProcessCore front end on its own signal (ns_core.c:1225-1267)
+      blockInd = HIw[kH_blockInd];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hp[u];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[0][u];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? scr[lane + G::kL * j] : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < G::kHP) hp[u] = scr[G::kFP + lane + 32 * u];
+      __syncwarp();
+      energy1 = 0.f;
+      if (lane < G::kL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 w = reinterpret_cast<const float2*>(s_win)[lane + G::kL * j];
+          v[j].x *= w.x;
+          v[j].y *= w.y;
+          energy1 += v[j].x * v[j].x + v[j].y * v[j].y;
+        }
+      }
+      energy1 = warp_sum(energy1);
+      if (energy1 != 0.f) {
+        warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
+        if (lane < G::kL) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
+          const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
+          const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
+          const float2 w = s_tw[k * (256 / ANA)];
+          const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+          const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
+          re[j] = er + (orr * w.x - oi * w.y);
+          im[j] = ei + (orr * w.y + oi * w.x);
+          if (nyq || k == 0) im[j] = 0.f;
+          magn[j] = sqrtf(re[j] * re[j] + im[j] * im[j]) + 1.f;
+          const float* R = B + k * kNsfBinRec;
+          noise[j] = X_noise[k];
+          prob[j] = X_prob[k];
+          parametric[j] = X_param[k];
+          // ComputeDdBasedWienerFilter's previous estimate (ns_core.c:993-994)
+          prevEst[j] = fdiv(X_magnP[k], R[kB_noisePrev] + 0.0001f) * R[kB_smooth];
+        }
+        __syncwarp();  // scratch is free again
+        prior = Hw[kH_priorSpeechProb];
+      }
+    }
+
+    if (energy1 == 0.f) {
+      // ---- zero input to Process (ns_core.c:1239-1264): flush the overlap, high bands pass
+      // through the delay line ungained.
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int pr = lane + 32 * u;
+        o0[u] = (u < 2 && pr < G::kHP) ? sy[u < 2 ? u : 0] : make_float2(0.f, 0.f);
+      }
+      sy[0] = sy[1] = make_float2(0.f, 0.f);
+    } else {
+      // ======== WebRtcNs_ProcessCore from the Wiener filter on
       // ---- (k) Wiener filter, flooring, start-up blend (ns_core.c:985-1007, 1268-1307)
       float hbProbSum = 0.f, hbGainSum = 0.f;
+      float sumMagnA = 0.f, sumMagnP = 0.f;   // split mode, high bands (ns_core.c:1376-1382)
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
@@ -684,7 +830,14 @@ nsf_process_kernel(const NsfLaunch p) {
         if (!nyq || lane == 0) {
           float* R = B + k * kNsfBinRec;
           R[kB_smooth] = flt;
-          *reinterpret_cast<float4*>(R + 8) = make_float4(noise[j], magn[j], logLrt[j], mpause[j]);
+          if (SPLIT) {
+            // ns_core.c:1309-1310: magnPrevProcess = magn, noisePrev = noise
+            if (NB > 1) { sumMagnA += R[kB_magnPrev]; sumMagnP += magn[j]; }
+            R[kB_noisePrev] = noise[j];
+            X_magnP[k] = magn[j];
+          } else {
+            *reinterpret_cast<float4*>(R + 8) = make_float4(noise[j], magn[j], logLrt[j], mpause[j]);
+          }
           scr[k] = make_float2(re[j], im[j]);
         }
         if (NB > 1) {
@@ -714,7 +867,7 @@ nsf_process_kernel(const NsfLaunch p) {
         }
       }
       __syncwarp();
-      warp_fft<G::kNC, -1>(v, scr, s_tw, lane);
+      warp_fft<G::kNC, -1>(v, scr, s_tw, s_tw12, lane);
       if (lane < G::kL) {
         const float sc = 2.f / (float)ANA;
 #pragma unroll
@@ -779,6 +932,10 @@ nsf_process_kernel(const NsfLaunch p) {
         warp_sum2(hbProbSum, hbGainSum);
         float avgProb = hbProbSum / (float)d;
         // sumMagnProcess / sumMagnAnalyze == 1 when Analyze and Process see one frame
+        if (SPLIT) {
+          warp_sum2(sumMagnA, sumMagnP);
+          avgProb *= sumMagnP / sumMagnA;
+        }
         const float avgGain = hbGainSum / (float)d;
         const float tmp = 2.f * avgProb - 1.f;
         const float gmod = 0.5f * (1.f + tanhf(tmp));
@@ -829,6 +986,10 @@ nsf_process_kernel(const NsfLaunch p) {
     for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int u = 0; u < kU; ++u) cur[b][u] = nxt[b][u];
+    if (SPLIT) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) curA[u] = nxtA[u];
+    }
     __syncwarp();
     { float* t = Hr; Hr = Hw; Hw = t; }
   }
@@ -836,7 +997,13 @@ nsf_process_kernel(const NsfLaunch p) {
   // ---- state: shared / registers -> HBM
   if (!state_ready) async_copy_wait_all();
   __syncwarp();
-  gS[lane] = Hr[lane];
+  // the fused kernel does not maintain the split-mode arrays: mark them stale
+  gS[lane] = (lane == kH_splitValid && p.frames > 0) ? __int_as_float(SPLIT ? 1 : 0) : Hr[lane];
+  if (SPLIT) {
+    float4* xd = reinterpret_cast<float4*>(gS + kNsfOffAux);
+    const float4* xs = reinterpret_cast<const float4*>(X_noise);
+    for (int i = lane; i < 4 * kNsfAuxStride / 4; i += 32) xd[i] = xs[i];
+  }
   {
     float4* dst = reinterpret_cast<float4*>(gS + kNsfOffBins);
     const float4* src = reinterpret_cast<const float4*>(B);
@@ -848,6 +1015,7 @@ nsf_process_kernel(const NsfLaunch p) {
     if (pr < G::kHP) {
       reinterpret_cast<float2*>(gS + kNsfOffXHist)[pr] = hx[u];
       reinterpret_cast<float2*>(gS + kNsfOffSynt)[pr] = sy[u];
+      if (SPLIT) reinterpret_cast<float2*>(gS + kNsfOffPHist)[pr] = hp[u];
 #pragma unroll
       for (int b = 0; b < NB - 1; ++b) reinterpret_cast<float2*>(gS + kNsfOffHb + 96 * b)[pr] = hb[b][u];
     }

@@ -16,6 +16,7 @@ enum : int {
   kH_counter = 2,        // int[3] :69
   kH_modelUpd0 = 5,      // int   modelUpdatePars[0] :82
   kH_modelUpd3 = 6,      // int   modelUpdatePars[3]
+  kH_splitValid = 7,     // int   1: the split-mode arrays below (kNsfOffSplit) are current
   kH_priorPars = 8,      // float[7] priorModelPars :84
   kH_priorSpeechProb = 15,
   kH_feat = 16,          // float[7] featureData :93
@@ -36,7 +37,14 @@ enum : int {
   kNsfOffInitMagn = kNsfOffHb + 192, // 132 floats: initMagnEst
   kNsfOffBins = kNsfOffInitMagn + 132,  // 129 x 12 floats
   kNsfBinRec = 12,
-  kNsfStateWordsRaw = kNsfOffBins + 129 * kNsfBinRec,
+  kNsfFusedWordsRaw = kNsfOffBins + 129 * kNsfBinRec,
+  // Split mode only (Analyze and Process fed different signals): what the
+  // fused kernel never needs because it is implied when both see one frame.
+  kNsfOffSplit = (kNsfFusedWordsRaw + 31) / 32 * 32,
+  kNsfOffPHist = kNsfOffSplit,       // 96 floats: last samples of dataBuf (kNsfOffXHist is analyzeBuf then)
+  kNsfOffAux = kNsfOffPHist + 96,    // 4 x 132 floats: noise | speechProb | parametricNoise | magnPrevProcess
+  kNsfAuxStride = 132,               //   (the record's magnPrev is magnPrevAnalyze then; ns_core.h:64-66,105-107)
+  kNsfStateWordsRaw = kNsfOffAux + 4 * kNsfAuxStride,
   kNsfStateWords = (kNsfStateWordsRaw + 31) / 32 * 32,  // 128-byte aligned slabs
   kNsfHistWords = 3008,  // 3 x 1000 int32, padded to 128 B
 };
@@ -63,6 +71,8 @@ struct NsfLaunch {
   const NsfTables* tables;
   const void* in;          // int16 or float samples
   void* out;
+  const void* ana_in;      // split mode: band-0 frames for Analyze (same sample type as `in`)
+  long long ana_stream_stride, ana_frame_stride;
   long long in_stream_stride, in_frame_stride, in_band_stride;     // in elements
   long long out_stream_stride, out_frame_stride, out_band_stride;
   int n_streams;

@@ -99,6 +99,27 @@ int WebRtcNs_ProcessBatchBandsF32(NsHandle* const* handles, int n_streams, int n
                                   const float* in, size_t in_stream_stride, float* out,
                                   size_t out_stream_stride, int frames);
 /*
+ * Analyze and Process fed different signals (float suppressor): full APM places the echo
+ * canceller between WebRtcNs_Analyze and WebRtcNs_Process (audio_processing_impl.cc:625-631), so
+ * the noise statistics come from `analyze_in` while `pcm_in` is what gets filtered.  The
+ * single-stream WebRtcNs_Analyze / WebRtcNs_Process pair does the same when their frames differ.
+ * Full-band int16 PCM versions: 8 and 16 kHz (one band); all handles on one GPU.  Band-frame
+ * float version: any rate, analyze_in holds band-0 frames [stream][frame][frame_len].
+ * A stream that has been driven this way stays on the two-signal kernel (later fused calls feed
+ * the Process signal to both sides, with results identical to the reference's).
+ */
+int WebRtcNs_AnalyzeProcessBatch(NsHandle* const* handles, int n_streams, const int16_t* analyze_in,
+                                 size_t analyze_stride, const int16_t* pcm_in, size_t in_stride,
+                                 int16_t* pcm_out, size_t out_stride, int frames);
+int WebRtcNs_AnalyzeProcessBatchDevice(NsHandle* const* handles, int n_streams,
+                                       const int16_t* analyze_in, size_t analyze_stride,
+                                       const int16_t* pcm_in, size_t in_stride, int16_t* pcm_out,
+                                       size_t out_stride, int frames, void* cuda_stream);
+int WebRtcNs_AnalyzeProcessBatchBandsF32(NsHandle* const* handles, int n_streams, int num_bands,
+                                         const float* analyze_in, size_t analyze_stream_stride,
+                                         const float* in, size_t in_stream_stride, float* out,
+                                         size_t out_stream_stride, int frames);
+/*
  * Interleaved multi-channel capture block, processed in place: the job of the author's wrapper
  * APM_NS::processCaptureStream (libapm/src/apm_ns.cpp:91-132 short, :47-89 float) -- deinterleave
  * (float samples in [-1, 1] through FloatToS16, audio_util.h:27-32), band split, Analyze + Process

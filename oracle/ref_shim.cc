@@ -90,6 +90,33 @@ int ref_ns_run(int fs, int mode, int nframes, const int16_t* pcm_in,
   return 0;
 }
 
+// Float NS with different signals for Analyze and Process (an echo canceller between them:
+// audio_processing_impl.cc:625-631), straight through the reference API.  ana: [frame][fl] band-0
+// frames for WebRtcNs_Analyze; in/out: [frame][band][fl] band frames for WebRtcNs_Process
+// (int16-scale floats).  The first fused_frames frames feed band 0 of `in` to both.
+int ref_ns_split_run(int fs, int mode, int nb, int nframes, int fused_frames, const float* ana,
+                     const float* in, float* out) {
+  NsHandle* h = NULL;
+  if (WebRtcNs_Create(&h) != 0) return -1;
+  if (WebRtcNs_Init(h, (uint32_t)fs) != 0 || WebRtcNs_set_policy(h, mode) != 0) {
+    WebRtcNs_Free(h);
+    return -1;
+  }
+  const int fl = fs == 8000 ? 80 : 160;
+  for (int f = 0; f < nframes; ++f) {
+    const float* bands_in[3];
+    float* bands_out[3];
+    for (int b = 0; b < nb; ++b) {
+      bands_in[b] = in + ((size_t)f * nb + b) * fl;
+      bands_out[b] = out + ((size_t)f * nb + b) * fl;
+    }
+    WebRtcNs_Analyze(h, f < fused_frames ? bands_in[0] : ana + (size_t)f * fl);
+    WebRtcNs_Process(h, bands_in, nb, bands_out);
+  }
+  WebRtcNs_Free(h);
+  return 0;
+}
+
 // Fixed NSx over one stream (explicit band split at 32/48 kHz, as
 // noise_suppression_impl.cc:90-93 would do; the author's -DNS_FIXED driver
 // never splits -- SURVEY.md appendix B.9).

@@ -38,6 +38,16 @@ class RefLib:
         assert rc == 0
         return (of if fs <= 16000 else None), oi, pp
 
+    def ns_split(self, fs, mode, ana, x, nb=1, fused_frames=0):
+        """Analyze fed `ana` [frames*fl] float, Process fed `x` [frames][nb][fl] float -> float out like x."""
+        fl = 80 if fs == 8000 else 160
+        ana = np.ascontiguousarray(ana, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        nfr = ana.size // fl
+        out = np.zeros_like(x)
+        assert self.lib.ref_ns_split_run(fs, mode, nb, nfr, fused_frames, _ptr(ana), _ptr(x), _ptr(out)) == 0
+        return out
+
     def nsx(self, fs, mode, pcm):
         fl = fs // 100
         nfr = len(pcm) // fl

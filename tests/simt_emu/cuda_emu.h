@@ -103,6 +103,8 @@ inline void __threadfence() { __sync_synchronize(); }
 inline int atomicAdd(int* p, int v) { return __sync_fetch_and_add(p, v); }
 template <typename T> inline T __ldcg(const T* p) { return *p; }
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline unsigned __brev(unsigned x) {

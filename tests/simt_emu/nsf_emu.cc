@@ -9,20 +9,26 @@
 #include "../../audiosignalprocess_b200/csrc/nsf_kernel.cuh"
 
 namespace nsb200 {
-float4 nsf_smem4[(kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWords) / 4 + 4];
+float4 nsf_smem4[(kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWordsSplit) / 4 + 4];
 }
 
 namespace {
 using namespace nsb200;
 
-template <int ANA, int NB, bool I16>
-void Tramp(void* a) { nsf_process_kernel<ANA, NB, I16>(*(const NsfLaunch*)a); }
+template <int ANA, int NB, bool I16, bool SPLIT = false>
+void Tramp(void* a) { nsf_process_kernel<ANA, NB, I16, SPLIT>(*(const NsfLaunch*)a); }
 
 typedef void (*Fn)(void*);
 Fn Pick(int ana, int nb, bool i16) {
 #define C(A, N) if (ana == A && nb == N) return i16 ? (Fn)Tramp<A, N, true> : (Fn)Tramp<A, N, false>;
   C(256, 1) C(256, 2) C(256, 3) C(128, 1)
 #undef C
+  return NULL;
+}
+Fn PickSplit(int ana, int nb) {
+  if (ana == 256 && nb == 1) return (Fn)Tramp<256, 1, false, true>;
+  if (ana == 256 && nb == 2) return (Fn)Tramp<256, 2, false, true>;
+  if (ana == 128 && nb == 1) return (Fn)Tramp<128, 1, false, true>;
   return NULL;
 }
 }  // namespace
@@ -68,6 +74,50 @@ int emu_nsf_run(int fs, int mode, int nb, int i16, int nstreams, int nframes, in
       for (int s = 0; s < nstreams; ++s)
         prior_prob[(size_t)s * nframes + f0] =
             ((float*)&state[(size_t)slots[s] * kNsfStateWords])[kH_priorSpeechProb];
+  }
+  return 0;
+}
+
+// Split mode (float samples): Analyze sees ana[stream][frame][fl], Process sees in[stream][frame][band][fl].
+// The first `fused_frames` frames run through the fused kernel on `in` (ana ignored) so that the
+// fused -> split hand-over of a running stream is exercised.
+int emu_nsf_run_split(int fs, int mode, int nb, int nstreams, int nframes, int fpl, int fused_frames,
+                      const float* ana_in, const float* in, float* out) {
+  const int ana = fs == 8000 ? 128 : 256;
+  const int fl = fs == 8000 ? 80 : 160;
+  Fn fs_fn = PickSplit(ana, nb), ff_fn = Pick(ana, nb, false);
+  if (!fs_fn || !ff_fn) return -1;
+  NsfTables tables;
+  nsf_fill_tables(&tables);
+  std::vector<uint32_t> state((size_t)nstreams * kNsfStateWords);
+  std::vector<int> hist((size_t)nstreams * kNsfHistWords, 0);
+  std::vector<int> slots(nstreams);
+  for (int s = 0; s < nstreams; ++s) {
+    slots[s] = s;
+    nsf_init_state(&state[(size_t)s * kNsfStateWords], (uint32_t)fs);
+    nsf_set_mode(&state[(size_t)s * kNsfStateWords], mode);
+  }
+  for (int f0 = 0; f0 < nframes;) {
+    const bool fused = f0 < fused_frames;
+    int nf = nframes - f0 < fpl ? nframes - f0 : fpl;
+    if (fused && f0 + nf > fused_frames) nf = fused_frames - f0;
+    NsfLaunch p;
+    p.state = (float*)state.data();
+    p.hist = hist.data();
+    p.slots = slots.data();
+    p.tables = &tables;
+    p.in = in + (size_t)f0 * nb * fl;
+    p.out = out + (size_t)f0 * nb * fl;
+    p.in_stream_stride = p.out_stream_stride = (long long)nframes * nb * fl;
+    p.in_frame_stride = p.out_frame_stride = (long long)nb * fl;
+    p.in_band_stride = p.out_band_stride = fl;
+    p.ana_in = ana_in + (size_t)f0 * fl;
+    p.ana_stream_stride = (long long)nframes * fl;
+    p.ana_frame_stride = fl;
+    p.n_streams = nstreams;
+    p.frames = nf;
+    simt_emu::launch(fused ? ff_fn : fs_fn, &p, (nstreams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta, kNsfWarpsPerCta * 32);
+    f0 += nf;
   }
   return 0;
 }

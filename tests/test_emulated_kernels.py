@@ -55,3 +55,38 @@ def test_nsf_kernel_source_within_tolerance(emu, oracle, nslib_host_synth, fs, m
         assert r[1], "stream %d outside envelope: %.3f LSB %.1f dB" % (s, r[2], r[3])
         strict += r[0]
     assert strict >= 3
+
+
+def split_signals(synth, n, fs, frames, nb=1):
+    """Process signal = stream s; Analyze signal = the same plus an 'echo' (another stream at half
+    level) that a canceller would have removed in between.  Frames 20-24 of the Analyze signal and
+    40-44 of the Process signal are digital silence (the two zero-energy early-outs, apart)."""
+    fl = 80 if fs == 8000 else 160
+    a = synth(n, fs, frames * fl, first_stream=2).astype(np.float32)
+    e = synth(n, fs, frames * fl, first_stream=11).astype(np.float32)
+    x = np.zeros((n, frames, nb, fl), np.float32)
+    x[:, :, 0, :] = a.reshape(n, frames, fl)
+    for b in range(1, nb):
+        x[:, :, b, :] = 0.25 * synth(n, fs, frames * fl, first_stream=20 + b).astype(np.float32).reshape(n, frames, fl)
+    ana = (a + 0.5 * e).reshape(n, frames, fl)
+    ana[:, 20:25] = 0.0
+    x[:, 40:45] = 0.0
+    return np.ascontiguousarray(ana.reshape(n, frames * fl)), np.ascontiguousarray(x)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("fs,mode,nb,fpl,fused", [(16000, 2, 1, 9, 0), (16000, 1, 2, 80, 30), (8000, 3, 1, 1, 0)])
+def test_nsf_split_kernel_source_against_reference(emu, reflib, nslib_host_synth, fs, mode, nb, fpl, fused):
+    """Analyze and Process fed different signals against the compiled
+    reference driven through its own API, including a stream handed over from the fused kernel."""
+    n, frames = 4, 80
+    ana, x = split_signals(nslib_host_synth, n, fs, frames, nb)
+    out = np.zeros_like(x)
+    assert emu.emu_nsf_run_split(fs, mode, nb, n, frames, fpl, fused, _ptr(ana), _ptr(x), _ptr(out)) == 0
+    strict = 0
+    for s in range(n):
+        ref = reflib.ns_split(fs, mode, ana[s], x[s], nb, fused)
+        r = judge_float(ref.ravel(), out[s].ravel())
+        assert r[1], "stream %d outside envelope: %.3f LSB %.1f dB" % (s, r[2], r[3])
+        strict += r[0]
+    assert strict >= 3
