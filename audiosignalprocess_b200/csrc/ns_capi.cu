@@ -852,9 +852,12 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   int chunk = frames;
   {
     const double bytes_per_frame = (double)n * fl * sizeof(int16_t);
-    int c = (int)(12.0e6 / bytes_per_frame + 0.5);
-    if (c < 5) c = 5;
-    if (frames >= 16 && c > (frames + 3) / 4) c = (frames + 3) / 4;
+    // ~12 MB per chunk, but at least four chunks when the call is big enough for 1.5 MB chunks
+    double target = 12.0e6;
+    if (bytes_per_frame * frames / 4.0 < target) target = bytes_per_frame * frames / 4.0;
+    if (target < 1.5e6) target = 1.5e6;
+    int c = (int)(target / bytes_per_frame + 0.5);
+    if (c < 1) c = 1;
     if (c > 250) c = 250;
     if (const char* e = getenv("NSB200_CHUNK_FRAMES")) {
       const int v = atoi(e);
