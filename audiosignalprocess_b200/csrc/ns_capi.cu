@@ -417,7 +417,7 @@ int SetPolicy(void* hv, int mode, uint32_t magic) {
 template <int ANA, int NB, bool I16, bool SPLIT>
 int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   const int grid = (p.n_streams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
-  const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * (SPLIT ? kNsfWarpWordsSplit : kNsfWarpWords));
+  const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * NsfWarpWords<SPLIT, NB>::value);
   if (smem > 48 * 1024)
     CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nsf_process_kernel<ANA, NB, I16, SPLIT><<<grid, kNsfWarpsPerCta * 32, smem, st>>>(p);
@@ -1147,6 +1147,20 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
       const float v = __uint_as_float((h1 & 0x807fffffu) | (((h1 >> 23) % 24u + 120u) << 23));   // |v| in [2^-7, 2^17)
       const int want = v > 0.f ? (v >= 32766.5f ? 32767 : (int)(v + 0.5f)) : (v <= -32767.5f ? -32768 : (int)(v - 0.5f));
       if (round_s16(v) != want) ++mism;
+    }
+    {
+      // nsb_logf == logf on [1, 2^40) (spectral magnitudes + 1, 1 + 2 snrPrior)
+      const float x = __uint_as_float((h1 & 0x007fffffu) | (((h2 >> 9) % 40u + 127u) << 23));
+      if (__float_as_uint(nsb_logf(x)) != __float_as_uint(logf(x))) ++mism;
+      const float x1 = 1.f + __uint_as_float((h2 & 0x007fffffu) | (((h1 >> 9) % 30u + 97u) << 23));  // just above 1
+      if (__float_as_uint(nsb_logf(x1)) != __float_as_uint(logf(x1))) ++mism;
+    }
+    {
+      // nsb_sqrtf_p1 == sqrtf + 1 on [0, 2^70): squared spectral magnitudes incl. the tiny end
+      const float x = __uint_as_float((h2 & 0x007fffffu) | (((h1 >> 7) % 140u + 57u) << 23));
+      if (__float_as_uint(nsb_sqrtf_p1(x)) != __float_as_uint(__fadd_rn(__fsqrt_rn(x), 1.f))) ++mism;
+      const float xs = __uint_as_float(h1 & 0x00ffffffu);   // subnormals and the smallest normals
+      if (nsb_sqrtf_p1(xs) != 1.f || nsb_sqrtf_p1(0.f) != 1.f) ++mism;
     }
     const float c = (float)(h1 % 401u);   // small integers as in counters
     if (__float_as_uint(fdiv(c, (float)(h2 % 200u + 1u))) != __float_as_uint(__fdiv_rn(c, (float)(h2 % 200u + 1u)))) ++mism;

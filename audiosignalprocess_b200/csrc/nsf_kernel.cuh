@@ -43,8 +43,16 @@ constexpr int kNsfWarpsPerCta = NSF_WARPS_PER_CTA;
 #endif
 constexpr int kNsfCtasPerSm = NSF_CTAS_PER_SM;
 constexpr int kNsfCtaTableWords = 912 + 2 * kFftTw12F2;  // win 256 | tw 512 | logi 132 | pad | regrouped twiddles 240
-constexpr int kNsfWarpWords = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2;
-constexpr int kNsfWarpWordsSplit = kNsfWarpWords + 4 * kNsfAuxStride;   // + noise | speechProb | parametric | magnPrevProcess
+// Per-warp shared memory (32-bit words): header x2 | bin records | FFT scratch | analysis block
+// (256) | synthesis overlap (96) | split: aux arrays + Process block (256) | high-band delay blocks.
+// The sample histories live in shared memory, not registers: the register budget of the per-bin
+// phases decides how far ptxas can interleave their dependent division chains.
+constexpr int kNsfWarpWordsBase = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2 + 256 + 96;
+template <bool SPLIT, int NB>
+struct NsfWarpWords {
+  static constexpr int value = kNsfWarpWordsBase + (SPLIT ? 4 * kNsfAuxStride + 256 : 0) + (NB - 1) * 256;
+};
+constexpr int kNsfWarpWordsMax = NsfWarpWords<true, 3>::value;
 
 template <int ANA>
 struct NsfGeo {
@@ -68,6 +76,22 @@ NSB_DEV int round_s16(float v) {  // FloatS16ToS16, common_audio/include/audio_u
   // v -+ 0.5 is exact below 2^15, so truncating first and clamping after gives the same integers.
   const int r = (int)(v + copysignf(0.5f, v));
   return r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
+}
+
+// One 32-bit-lane PCM word as it sits in memory: two int16 samples, or a float pair.
+template <bool I16> struct PcmWordT { typedef float2 type; };
+template <> struct PcmWordT<true> { typedef uint32_t type; };
+template <bool I16>
+NSB_DEV void pcm_load(float2& dst, const void* base, size_t off, int w) {
+  dst = reinterpret_cast<const float2*>(static_cast<const float*>(base) + off)[w];
+}
+template <bool I16>
+NSB_DEV void pcm_load(uint32_t& dst, const void* base, size_t off, int w) {
+  dst = reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(base) + off)[w];
+}
+NSB_DEV float2 pcm_unpack(float2 v) { return v; }
+NSB_DEV float2 pcm_unpack(uint32_t v) {
+  return make_float2((float)(int16_t)(v & 0xffffu), (float)(int16_t)(v >> 16));
 }
 
 // ---- threshold re-estimation every 500 frames (ns_core.c:337-517), warp parallel.
@@ -203,7 +227,7 @@ nsf_process_kernel(const NsfLaunch p) {
   const int sidx = (int)blockIdx.x * kNsfWarpsPerCta + warp;
   if (sidx >= p.n_streams) return;  // whole warp leaves; no block barriers below
 
-  float* W = smem + kNsfCtaTableWords + warp * (SPLIT ? kNsfWarpWordsSplit : kNsfWarpWords);
+  float* W = smem + kNsfCtaTableWords + warp * NsfWarpWords<SPLIT, NB>::value;
   // Header scalars are double buffered: within a frame every lane reads the
   // frame-start copy (Hr) and writes the next copy (Hw) with warp-uniform
   // values, so there is never a read-modify-write race between lanes.
@@ -211,10 +235,14 @@ nsf_process_kernel(const NsfLaunch p) {
   float* Hw = W + kNsfHdrWords;
   float* B = W + 2 * kNsfHdrWords;            // per-bin records
   float2* scr = reinterpret_cast<float2*>(B + 129 * kNsfBinRec);  // FFT scratch (8-byte aligned)
-  float* X_noise = B + 129 * kNsfBinRec + 2 * kFftScratchF2;       // split mode: self->noise
+  float2* blkA = scr + kFftScratchF2;          // analysis block [history | frame], 128 pairs (analyzeBuf)
+  float2* ovl = blkA + 128;                    // synthesis overlap, 48 pairs (head of syntBuf)
+  float* X_noise = reinterpret_cast<float*>(ovl + 48);              // split mode: self->noise
   float* X_prob = X_noise + kNsfAuxStride;                          //   self->speechProb
   float* X_param = X_prob + kNsfAuxStride;                          //   self->parametricNoise
   float* X_magnP = X_param + kNsfAuxStride;                         //   self->magnPrevProcess
+  float2* blkP = reinterpret_cast<float2*>(X_magnP + kNsfAuxStride);  // split mode: Process block (dataBuf)
+  float2* blkH = reinterpret_cast<float2*>(reinterpret_cast<float*>(ovl + 48) + (SPLIT ? 4 * kNsfAuxStride + 256 : 0));  // high-band delay blocks (dataBufHB)
 
   const int slot = p.slots[sidx];
   float* gS = p.state + (size_t)slot * kNsfStateWords;
@@ -235,23 +263,17 @@ nsf_process_kernel(const NsfLaunch p) {
     }
   }
   bool state_ready = false;
-  float2 hx[2], sy[2];       // analysis history / synthesis overlap, pair p = lane + 32u
-  float2 hp[2];              // split mode: history of the Process signal (dataBuf)
-  float2 hb[NB > 1 ? NB - 1 : 1][2];
+  // sample histories: the tail of each block is what the previous frame left behind
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int pr = lane + 32 * u;
-    hx[u] = sy[u] = make_float2(0.f, 0.f);
     if (pr < G::kHP) {
-      hx[u] = reinterpret_cast<const float2*>(gS + kNsfOffXHist)[pr];
-      sy[u] = reinterpret_cast<const float2*>(gS + kNsfOffSynt)[pr];
-    }
-    hp[u] = make_float2(0.f, 0.f);
-    if (SPLIT && pr < G::kHP) hp[u] = reinterpret_cast<const float2*>(gS + kNsfOffPHist)[pr];
+      blkA[G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffXHist)[pr];
+      ovl[pr] = reinterpret_cast<const float2*>(gS + kNsfOffSynt)[pr];
+      if (SPLIT) blkP[G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffPHist)[pr];
 #pragma unroll
-    for (int b = 0; b < NB - 1; ++b) {
-      hb[b][u] = make_float2(0.f, 0.f);
-      if (pr < G::kHP) hb[b][u] = reinterpret_cast<const float2*>(gS + kNsfOffHb + 96 * b)[pr];
+      for (int b = 0; b < NB - 1; ++b)
+        blkH[128 * b + G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffHb + 96 * b)[pr];
     }
   }
   __syncwarp();
@@ -268,8 +290,7 @@ nsf_process_kernel(const NsfLaunch p) {
         X_prob[k] = 0.f;
         X_param[k] = 0.f;
       }
-      hp[0] = hx[0];
-      hp[1] = hx[1];
+      for (int pr = lane; pr < G::kHP; pr += 32) blkP[G::kFP + pr] = blkA[G::kFP + pr];
       __syncwarp();
     }
   }
@@ -285,24 +306,19 @@ nsf_process_kernel(const NsfLaunch p) {
   const size_t out_base = (size_t)sidx * (size_t)p.out_stream_stride;
   constexpr int kU = (G::kFP + 31) / 32;  // words per lane per band-frame (3 / 2)
 
-  // Raw frame words, prefetched one frame ahead.
-  float2 cur[NB][kU];
-  auto load_frame = [&](int f, float2 (&dst)[NB][kU]) {
+  // Raw frame words (two int16 samples, or a float pair), prefetched one frame ahead and
+  // converted where they are used: converting at the load would wait for it on the spot.
+  typedef typename PcmWordT<I16>::type PcmWord;
+  PcmWord cur[NB][kU];
+  auto load_frame = [&](int f, PcmWord (&dst)[NB][kU]) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const size_t off = in_base + (size_t)f * (size_t)p.in_frame_stride + (size_t)b * (size_t)p.in_band_stride;
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int w = lane + 32 * u;
-        dst[b][u] = make_float2(0.f, 0.f);
-        if (w < G::kFP) {
-          if (I16) {
-            const uint32_t v = reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.in) + off)[w];
-            dst[b][u] = make_float2((float)(int16_t)(v & 0xffffu), (float)(int16_t)(v >> 16));
-          } else {
-            dst[b][u] = reinterpret_cast<const float2*>(static_cast<const float*>(p.in) + off)[w];
-          }
-        }
+        dst[b][u] = PcmWord();
+        if (w < G::kFP) pcm_load<I16>(dst[b][u], p.in, off, w);
       }
     }
   };
@@ -317,21 +333,14 @@ nsf_process_kernel(const NsfLaunch p) {
   };
 
   // split mode: band-0 frame of the Analyze signal
-  float2 curA[kU];
-  auto load_ana = [&](int f, float2 (&dst)[kU]) {
+  PcmWord curA[kU];
+  auto load_ana = [&](int f, PcmWord (&dst)[kU]) {
     const size_t off = (size_t)sidx * (size_t)p.ana_stream_stride + (size_t)f * (size_t)p.ana_frame_stride;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int w = lane + 32 * u;
-      dst[u] = make_float2(0.f, 0.f);
-      if (w < G::kFP) {
-        if (I16) {
-          const uint32_t v = reinterpret_cast<const uint32_t*>(static_cast<const int16_t*>(p.ana_in) + off)[w];
-          dst[u] = make_float2((float)(int16_t)(v & 0xffffu), (float)(int16_t)(v >> 16));
-        } else {
-          dst[u] = reinterpret_cast<const float2*>(static_cast<const float*>(p.ana_in) + off)[w];
-        }
-      }
+      dst[u] = PcmWord();
+      if (w < G::kFP) pcm_load<I16>(dst[u], p.ana_in, off, w);
     }
   };
   if (p.frames > 0) load_frame(0, cur);
@@ -342,8 +351,8 @@ nsf_process_kernel(const NsfLaunch p) {
   const bool cta_sync = NSF_FRAME_SYNC && ((int)blockIdx.x + 1) * kNsfWarpsPerCta <= p.n_streams;
   for (int f = 0; f < p.frames; ++f) {
     if (cta_sync) __syncthreads();
-    float2 nxt[NB][kU] = {};
-    float2 nxtA[kU] = {};
+    PcmWord nxt[NB][kU] = {};
+    PcmWord nxtA[kU] = {};
     if (f + 1 < p.frames) load_frame(f + 1, nxt);
     if (SPLIT && f + 1 < p.frames) load_ana(f + 1, nxtA);
 
@@ -353,20 +362,23 @@ nsf_process_kernel(const NsfLaunch p) {
 
     // ---- (a) UpdateBuffer: history | new frame -> scratch as sample pairs
     // (all input was read into registers above, so out may alias in: ns_core.c:1225,1357)
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hx[u];
-#pragma unroll
-    for (int u = 0; u < kU; ++u)
-      if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = SPLIT ? curA[u] : cur[0][u];
-    __syncwarp();
     float2 v[4];
+    {
+      float2 t[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? scr[lane + G::kL * j] : make_float2(0.f, 0.f);
+      for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < G::kHP) t[u] = blkA[G::kFP + lane + 32 * u];
+      __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (lane + 32 * u < G::kHP) hx[u] = scr[G::kFP + lane + 32 * u];
-    __syncwarp();
+      for (int u = 0; u < 2; ++u)
+        if (lane + 32 * u < G::kHP) blkA[lane + 32 * u] = t[u];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (lane + 32 * u < G::kFP) blkA[G::kHP + lane + 32 * u] = pcm_unpack(SPLIT ? curA[u] : cur[0][u]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? blkA[lane + G::kL * j] : make_float2(0.f, 0.f);
+    }
 
     // ---- (b) Windowing + Energy (ns_core.c:1070-1071 / 1237-1238)
     float energy1 = 0.f;
@@ -388,7 +400,7 @@ nsf_process_kernel(const NsfLaunch p) {
     // values handed from the analysis to the process part (fused: in registers; split: the
     // process part reloads them from the state it shares with Analyze)
     int blockInd = HIr[kH_blockInd];
-    float re[G::kSlots], im[G::kSlots], magn[G::kSlots];
+    float magn[G::kSlots];   // the spectrum itself waits in scratch (scr[k]) for the Wiener gain
     float noise[G::kSlots], prevEst[G::kSlots], parametric[G::kSlots], prob[G::kSlots];
     float noisePrev[G::kSlots], logLrt[G::kSlots], mpause[G::kSlots];
     float prior = 0.f;
@@ -410,26 +422,36 @@ nsf_process_kernel(const NsfLaunch p) {
 
       float lmagn[G::kSlots];
       float sigE = 0.f, sumMagn = 0.f;
+      {
+        float re[G::kSlots], im[G::kSlots];
 #pragma unroll
-      for (int j = 0; j < G::kSlots; ++j) {
-        const bool nyq = (j == G::kSlots - 1);
-        const int k = nyq ? G::kNC : lane + 32 * j;
-        const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
-        const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
-        const float2 w = s_tw[k * (256 / ANA)];
-        const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
-        const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
-        re[j] = er + (orr * w.x - oi * w.y);
-        im[j] = ei + (orr * w.y + oi * w.x);
-        if (nyq || k == 0) im[j] = 0.f;
-        magn[j] = sqrtf(re[j] * re[j] + im[j] * im[j]) + 1.f;
-        lmagn[j] = logf(magn[j]);
-        if (!nyq || lane == 0) {
-          sigE += re[j] * re[j] + im[j] * im[j];
-          sumMagn += magn[j];
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
+          const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
+          const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
+          const float2 w = s_tw[k * (256 / ANA)];
+          const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+          const float orr = 0.5f * (zk.y + zm.y), oi = -0.5f * (zk.x - zm.x);
+          re[j] = er + (orr * w.x - oi * w.y);
+          im[j] = ei + (orr * w.y + oi * w.x);
+          if (nyq || k == 0) im[j] = 0.f;
+          magn[j] = nsb_sqrtf_p1(re[j] * re[j] + im[j] * im[j]);
+          lmagn[j] = nsb_logf(magn[j]);
+          if (!nyq || lane == 0) {
+            sigE += re[j] * re[j] + im[j] * im[j];
+            sumMagn += magn[j];
+          }
+        }
+        __syncwarp();  // every lane has read its mirrored points: scratch is free again
+        if (!SPLIT) {
+#pragma unroll
+          for (int j = 0; j < G::kSlots; ++j) {
+            const bool nyq = (j == G::kSlots - 1);
+            if (!nyq || lane == 0) scr[nyq ? G::kNC : lane + 32 * j] = make_float2(re[j], im[j]);
+          }
         }
       }
-      __syncwarp();  // scratch is free again
       warp_sum2(sigE, sumMagn);
       const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
 
@@ -479,12 +501,24 @@ nsf_process_kernel(const NsfLaunch p) {
           if (fabsf(lmagn[j] - lq[s]) < 0.01f)
             dn[s] = fdiv_r(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s], rc1[s]);
         }
-        if (sel >= 0) quant = expf(sel == 0 ? lq[0] : (sel == 1 ? lq[1] : lq[2]));
         noise[j] = quant;
         if (!nyq || lane == 0) {
           *reinterpret_cast<float4*>(R) = make_float4(lq[0], lq[1], lq[2], dn[0]);
           // whole 16-byte groups only: scalar accesses at a 12-word lane stride are 4-way bank conflicts
           *reinterpret_cast<float4*>(R + 4) = make_float4(dn[1], dn[2], quant, r1.w);
+        }
+      }
+      // latch (every frame during start-up, then once per tracker period) outside the slot loop,
+      // so that the 15 tracker updates above form one block the scheduler can interleave
+      if (sel >= 0) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          float* R = B + (nyq ? G::kNC : lane + 32 * j) * kNsfBinRec;
+          const float q = expf(R[sel]);
+          noise[j] = q;
+          if (!nyq || lane == 0) R[kB_quantile] = q;
         }
       }
 
@@ -564,8 +598,9 @@ nsf_process_kernel(const NsfLaunch p) {
         logLrt[j] = r2.z;
         mpause[j] = r2.w;
         prevEst[j] = fdiv(r2.y, r2.x + 0.0001f) * smooth;
-        snrPost[j] = 0.f;
-        if (magn[j] > noise[j]) snrPost[j] = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
+        // branch-free: a branch per slot would fence the five division chains off from each other
+        const float post = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
+        snrPost[j] = magn[j] > noise[j] ? post : 0.f;
         snrPrior[j] = 0.98f * prevEst[j] + (1.f - 0.98f) * snrPost[j];
         if (!nyq || lane == 0) {
           sumPause += mpause[j];
@@ -581,7 +616,7 @@ nsf_process_kernel(const NsfLaunch p) {
         float den = sumMagn - __shfl_sync(kFullMask, magn[0], 0);
         den = NSB_FDIV_C(den, kMagnLenF);
         const float num = NSB_FDIV_C(sumLog, kMagnLenF);
-        const float sf = expf(num) / den;
+        const float sf = fdiv(expf(num), den);
         feat0 = Hr[kH_feat + 0];
         feat0 += 0.3f * (sf - feat0);
         Hw[kH_feat + 0] = feat0;
@@ -604,8 +639,8 @@ nsf_process_kernel(const NsfLaunch p) {
         varP = NSB_FDIV_C(varP, kMagnLenF);
         varM = NSB_FDIV_C(varM, kMagnLenF);
         float feat6 = Hr[kH_feat + 6] + signalEnergy;
-        float ad = varM - (cov * cov) / (varP + 0.0001f);
-        ad = ad / (feat5 + 0.0001f);
+        float ad = varM - fdiv(cov * cov, varP + 0.0001f);
+        ad = fdiv(ad, feat5 + 0.0001f);
         feat4 = Hr[kH_feat + 4];
         feat4 += 0.3f * (ad - feat4);
         Hw[kH_feat + 4] = feat4;
@@ -649,7 +684,7 @@ nsf_process_kernel(const NsfLaunch p) {
           const float t1 = 1.f + 2.f * snrPrior[j];
           const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
           const float bessel = (snrPost[j] + 1.f) * t2;
-          logLrt[j] += 0.5f * (bessel - logf(t1) - logLrt[j]);
+          logLrt[j] += 0.5f * (bessel - nsb_logf(t1) - logLrt[j]);
           if (!nyq || lane == 0) lsum += logLrt[j];
         }
         lsum = warp_sum(lsum);
@@ -675,7 +710,7 @@ nsf_process_kernel(const NsfLaunch p) {
         if (prior > 1.f) prior = 1.f;
         if (prior < 0.01f) prior = 0.01f;
         Hw[kH_priorSpeechProb] = prior;
-        const float gainPrior = (1.f - prior) / (prior + 0.0001f);
+        const float gainPrior = fdiv(1.f - prior, prior + 0.0001f);
 #pragma unroll
         for (int j = 0; j < G::kSlots; ++j) {
           float inv = expf(-logLrt[j]);
@@ -733,19 +768,22 @@ nsf_process_kernel(const NsfLaunch p) {
     if (SPLIT) {
       // ======== WebRtcNs_ProcessCore front end on its own signal (ns_core.c:1225-1267)
       blockInd = HIw[kH_blockInd];
+      {
+        float2 t[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hp[u];
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) t[u] = blkP[G::kFP + lane + 32 * u];
+        __syncwarp();
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[0][u];
-      __syncwarp();
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) blkP[lane + 32 * u] = t[u];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? scr[lane + G::kL * j] : make_float2(0.f, 0.f);
+        for (int u = 0; u < kU; ++u)
+          if (lane + 32 * u < G::kFP) blkP[G::kHP + lane + 32 * u] = pcm_unpack(cur[0][u]);
+        __syncwarp();
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (lane + 32 * u < G::kHP) hp[u] = scr[G::kFP + lane + 32 * u];
-      __syncwarp();
+        for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? blkP[lane + G::kL * j] : make_float2(0.f, 0.f);
+      }
       energy1 = 0.f;
       if (lane < G::kL) {
 #pragma unroll
@@ -764,6 +802,7 @@ nsf_process_kernel(const NsfLaunch p) {
           for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
         }
         __syncwarp();
+        float re[G::kSlots], im[G::kSlots];
 #pragma unroll
         for (int j = 0; j < G::kSlots; ++j) {
           const bool nyq = (j == G::kSlots - 1);
@@ -776,7 +815,7 @@ nsf_process_kernel(const NsfLaunch p) {
           re[j] = er + (orr * w.x - oi * w.y);
           im[j] = ei + (orr * w.y + oi * w.x);
           if (nyq || k == 0) im[j] = 0.f;
-          magn[j] = sqrtf(re[j] * re[j] + im[j] * im[j]) + 1.f;
+          magn[j] = nsb_sqrtf_p1(re[j] * re[j] + im[j] * im[j]);
           const float* R = B + k * kNsfBinRec;
           noise[j] = X_noise[k];
           prob[j] = X_prob[k];
@@ -785,6 +824,11 @@ nsf_process_kernel(const NsfLaunch p) {
           prevEst[j] = fdiv(X_magnP[k], R[kB_noisePrev] + 0.0001f) * R[kB_smooth];
         }
         __syncwarp();  // scratch is free again
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          if (!nyq || lane == 0) scr[nyq ? G::kNC : lane + 32 * j] = make_float2(re[j], im[j]);
+        }
         prior = Hw[kH_priorSpeechProb];
       }
     }
@@ -795,38 +839,56 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int pr = lane + 32 * u;
-        o0[u] = (u < 2 && pr < G::kHP) ? sy[u < 2 ? u : 0] : make_float2(0.f, 0.f);
+        o0[u] = make_float2(0.f, 0.f);
+        if (pr < G::kHP) {   // a lane re-reads only what it wrote itself
+          o0[u] = ovl[pr];
+          ovl[pr] = make_float2(0.f, 0.f);
+        }
       }
-      sy[0] = sy[1] = make_float2(0.f, 0.f);
     } else {
       // ======== WebRtcNs_ProcessCore from the Wiener filter on
       // ---- (k) Wiener filter, flooring, start-up blend (ns_core.c:985-1007, 1268-1307)
       float hbProbSum = 0.f, hbGainSum = 0.f;
       float sumMagnA = 0.f, sumMagnP = 0.f;   // split mode, high bands (ns_core.c:1376-1382)
+      float gainW[G::kSlots];
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
-        const bool nyq = (j == G::kSlots - 1);
-        const int k = nyq ? G::kNC : lane + 32 * j;
-        float cur_est = 0.f;
-        if (magn[j] > noise[j]) cur_est = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
+        const float post = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
+        const float cur_est = magn[j] > noise[j] ? post : 0.f;
         const float sp = 0.98f * prevEst[j] + (1.f - 0.98f) * cur_est;
-        float flt = fdiv(sp, overdrive + sp);
-        if (flt < denoiseBound) flt = denoiseBound;
-        if (flt > 1.f) flt = 1.f;
-        if (blockInd < 50) {
+        float g = fdiv(sp, overdrive + sp);
+        if (g < denoiseBound) g = denoiseBound;
+        if (g > 1.f) g = 1.f;
+        gainW[j] = g;
+      }
+      // the start-up blend sits outside the per-slot loops: a (warp-uniform) branch inside them
+      // would fence the slots' division chains off from each other
+      if (blockInd < 50) {
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          const bool nyq = (j == G::kSlots - 1);
+          const int k = nyq ? G::kNC : lane + 32 * j;
           float ime = gInitMagn[k] + magn[j];
           if (!nyq || lane == 0) gInitMagn[k] = ime;
           float ft = ime - overdrive * parametric[j];
           ft /= (ime + 0.0001f);
           if (ft < denoiseBound) ft = denoiseBound;
           if (ft > 1.f) ft = 1.f;
-          flt *= (float)blockInd;
+          float g = gainW[j] * (float)blockInd;
           ft *= (float)(50 - blockInd);
-          flt += ft;
-          flt /= 50.f;
+          g += ft;
+          g /= 50.f;
+          gainW[j] = g;
         }
-        re[j] *= flt;
-        im[j] *= flt;
+      }
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const int k = nyq ? G::kNC : lane + 32 * j;
+        const float flt = gainW[j];
+        float2 z = scr[k];   // written by this lane (the Nyquist point by lane 0)
+        z.x *= flt;
+        z.y *= flt;
         if (!nyq || lane == 0) {
           float* R = B + k * kNsfBinRec;
           R[kB_smooth] = flt;
@@ -838,7 +900,7 @@ nsf_process_kernel(const NsfLaunch p) {
           } else {
             *reinterpret_cast<float4*>(R + 8) = make_float4(noise[j], magn[j], logLrt[j], mpause[j]);
           }
-          scr[k] = make_float2(re[j], im[j]);
+          scr[k] = z;
         }
         if (NB > 1) {
           // averages over the top quarter of the band, bins [magnLen - d - 1, magnLen - 1)
@@ -917,13 +979,15 @@ nsf_process_kernel(const NsfLaunch p) {
         float2 o = make_float2(0.f, 0.f);
         if (pr < G::kFP) {
           o = scr[pr];
-          if (u < 2 && pr < G::kHP) { o.x += sy[u < 2 ? u : 0].x; o.y += sy[u < 2 ? u : 0].y; }
+          if (pr < G::kHP) {
+            const float2 t = ovl[pr];
+            o.x += t.x;
+            o.y += t.y;
+            ovl[pr] = scr[G::kFP + pr];
+          }
         }
         o0[u] = I16 ? o : make_float2(sat_s16f(o.x), sat_s16f(o.y));  // round_s16 saturates too
       }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (lane + 32 * u < G::kHP) sy[u] = scr[G::kFP + lane + 32 * u];
       __syncwarp();
 
       // ---- (n) high-band time-domain gain (ns_core.c:1362-1404)
@@ -958,26 +1022,28 @@ nsf_process_kernel(const NsfLaunch p) {
       // output = oldest kFrame samples of [history | new frame]
 #pragma unroll
       for (int b = 0; b < NB - 1; ++b) {
+        float2* blk = blkH + 128 * b;   // [delayed history | new frame]
+        float2 t[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) t[u] = blk[G::kFP + lane + 32 * u];
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-          if (lane + 32 * u < G::kHP) scr[lane + 32 * u] = hb[b][u];
+          if (lane + 32 * u < G::kHP) blk[lane + 32 * u] = t[u];
 #pragma unroll
         for (int u = 0; u < kU; ++u)
-          if (lane + 32 * u < G::kFP) scr[G::kHP + lane + 32 * u] = cur[b + 1 < NB ? b + 1 : 0][u];
+          if (lane + 32 * u < G::kFP) blk[G::kHP + lane + 32 * u] = pcm_unpack(cur[b + 1 < NB ? b + 1 : 0][u]);
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int pr = lane + 32 * u;
           if (pr < G::kFP) {
-            float2 o = scr[pr];
+            float2 o = blk[pr];
             if (hbApplyGain) { o.x *= hbGain; o.y *= hbGain; }
             store_pair(f, b + 1, pr, I16 ? o : make_float2(sat_s16f(o.x), sat_s16f(o.y)));
           }
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (lane + 32 * u < G::kHP) hb[b][u] = scr[G::kFP + lane + 32 * u];
       }
       __syncwarp();
     }
@@ -1013,11 +1079,12 @@ nsf_process_kernel(const NsfLaunch p) {
   for (int u = 0; u < 2; ++u) {
     const int pr = lane + 32 * u;
     if (pr < G::kHP) {
-      reinterpret_cast<float2*>(gS + kNsfOffXHist)[pr] = hx[u];
-      reinterpret_cast<float2*>(gS + kNsfOffSynt)[pr] = sy[u];
-      if (SPLIT) reinterpret_cast<float2*>(gS + kNsfOffPHist)[pr] = hp[u];
+      reinterpret_cast<float2*>(gS + kNsfOffXHist)[pr] = blkA[G::kFP + pr];
+      reinterpret_cast<float2*>(gS + kNsfOffSynt)[pr] = ovl[pr];
+      if (SPLIT) reinterpret_cast<float2*>(gS + kNsfOffPHist)[pr] = blkP[G::kFP + pr];
 #pragma unroll
-      for (int b = 0; b < NB - 1; ++b) reinterpret_cast<float2*>(gS + kNsfOffHb + 96 * b)[pr] = hb[b][u];
+      for (int b = 0; b < NB - 1; ++b)
+        reinterpret_cast<float2*>(gS + kNsfOffHb + 96 * b)[pr] = blkH[128 * b + G::kFP + pr];
     }
   }
 }

@@ -9,7 +9,7 @@
 #include "../../audiosignalprocess_b200/csrc/nsf_kernel.cuh"
 
 namespace nsb200 {
-float4 nsf_smem4[(kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWordsSplit) / 4 + 4];
+float4 nsf_smem4[(kNsfCtaTableWords + kNsfWarpsPerCta * kNsfWarpWordsMax) / 4 + 4];
 }
 
 namespace {
