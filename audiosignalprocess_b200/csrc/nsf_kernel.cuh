@@ -353,8 +353,6 @@ nsf_process_kernel(const NsfLaunch p) {
     if (cta_sync) __syncthreads();
     PcmWord nxt[NB][kU] = {};
     PcmWord nxtA[kU] = {};
-    if (f + 1 < p.frames) load_frame(f + 1, nxt);
-    if (SPLIT && f + 1 < p.frames) load_ana(f + 1, nxtA);
 
     const int* HIr = reinterpret_cast<const int*>(Hr);
     int* HIw = reinterpret_cast<int*>(Hw);
@@ -376,6 +374,14 @@ nsf_process_kernel(const NsfLaunch p) {
       for (int u = 0; u < kU; ++u)
         if (lane + 32 * u < G::kFP) blkA[G::kHP + lane + 32 * u] = pcm_unpack(SPLIT ? curA[u] : cur[0][u]);
       __syncwarp();
+      // The next frame's loads are issued only now, after this frame's words were consumed: the
+      // consumer waits on a scoreboard shared by every load this static instruction has in
+      // flight, so issuing the prefetch first made it wait for the prefetch itself (10 % of the
+      // kernel's stall samples sat on the int16 unpack above).
+      if (f + 1 < p.frames) {
+        load_frame(f + 1, nxt);
+        if (SPLIT) load_ana(f + 1, nxtA);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? blkA[lane + G::kL * j] : make_float2(0.f, 0.f);
     }
