@@ -45,6 +45,7 @@ SYMBOLS = {
     "WebRtcNsB200_LastError": (C.c_char_p, []),
     "WebRtcNsB200_KernelLaunches": (C.c_uint64, []),
     "WebRtcNsB200_SelfTest": (C.c_int, [C.c_uint64]),
+    "WebRtcNsB200_SelfTestStats": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "WebRtcNsB200_SynthPcmDevice": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "WebRtcNsB200_SynthPcmHost": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "WebRtcNsB200_ChecksumDevice": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -145,9 +145,13 @@ int WebRtcNsB200_Synchronize(void);
 const char* WebRtcNsB200_LastError(void);
 /* Kernels launched by this library since load (for bench.py's gpu_launches). */
 uint64_t WebRtcNsB200_KernelLaunches(void);
-/* Device self-test of the kernels' arithmetic shortcuts (branch-free IEEE division, floor
- * square root) against their exact definitions over n_cases operands.  0 = all identical. */
+/* Device self-test of the kernels' arithmetic shortcuts against their exact definitions over
+ * n_cases operands: logf, sqrtf, int16 rounding and the floor square root must be identical;
+ * the branch-free division must equal IEEE division except for at most 2 per million quotients
+ * that may be one ulp off (stats[0] = hard mismatches, stats[1] = divisions one ulp off,
+ * stats[2] = divisions checked).  0 = pass. */
 int WebRtcNsB200_SelfTest(uint64_t n_cases);
+int WebRtcNsB200_SelfTestStats(uint64_t n_cases, uint64_t* stats);
 /* Deterministic synthetic PCM (csrc/pcm_synth.h) written on the device:
  * stream s, sample n -> dst[s*stride + n], n < n_samples, as stream index
  * first_stream + s at time offset first_sample. */
