@@ -7,4 +7,5 @@ importing works anywhere, but every call needs the CUDA library and a GPU.
 from .capi import load_library, LIB_PATH  # noqa: F401
 from .ns import (  # noqa: F401
     NsError, NoiseSuppressor, NoiseSuppressorX, NsBatch, synth_pcm_host, frame_len, num_bands,
+    run_generated_job,
 )

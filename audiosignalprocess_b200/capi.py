@@ -49,6 +49,7 @@ SYMBOLS = {
     "WebRtcNsB200_SynthPcmDevice": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "WebRtcNsB200_SynthPcmHost": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "WebRtcNsB200_ChecksumDevice": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "WebRtcNsB200_ChecksumAccumulateDevice": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

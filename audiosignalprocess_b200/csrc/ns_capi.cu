@@ -1190,19 +1190,28 @@ int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_c
 
 __global__ void synth_kernel(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream,
                              uint32_t fs, uint32_t first_sample, uint32_t n_samples, uint32_t seed) {
-  const size_t pairs = n_samples / 2;
-  const size_t total = (size_t)n_streams * pairs;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t s = (uint32_t)(i / pairs);
-    const uint32_t n = (uint32_t)(i % pairs) * 2u;
-    const uint32_t a = (uint16_t)pcm_synth_sample(seed, first_stream + s, fs, first_sample + n);
-    const uint32_t b = (uint16_t)pcm_synth_sample(seed, first_stream + s, fs, first_sample + n + 1u);
+  // grid: x over sample pairs, y over streams (no per-element 64-bit index division)
+  const uint32_t pairs = n_samples / 2;
+  for (uint32_t s = blockIdx.y; s < (uint32_t)n_streams; s += gridDim.y)
+  for (uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += gridDim.x * blockDim.x) {
+    const uint32_t n = pr * 2u;
+    // the generator divides 64-bit times by fs: with fs a literal those become multiplications
+    uint32_t a, b;
+#define NSB_SYNTH_PAIR(FS)                                                                   \
+    a = (uint16_t)pcm_synth_sample(seed, first_stream + s, FS, first_sample + n);            \
+    b = (uint16_t)pcm_synth_sample(seed, first_stream + s, FS, first_sample + n + 1u)
+    if (fs == 16000u) { NSB_SYNTH_PAIR(16000u); }
+    else if (fs == 8000u) { NSB_SYNTH_PAIR(8000u); }
+    else if (fs == 32000u) { NSB_SYNTH_PAIR(32000u); }
+    else if (fs == 48000u) { NSB_SYNTH_PAIR(48000u); }
+    else { NSB_SYNTH_PAIR(fs); }
+#undef NSB_SYNTH_PAIR
     reinterpret_cast<uint32_t*>(dst + (size_t)s * stride)[n / 2] = a | (b << 16);
   }
 }
 
 __global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
-                                long long* sums) {
+                                long long* sums, int accumulate) {
   const int s = blockIdx.x;
   if (s >= n_streams) return;
   long long a = 0, b = 0;
@@ -1224,8 +1233,8 @@ __global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    sums[2 * s] = sa[0];
-    sums[2 * s + 1] = sb[0];
+    sums[2 * s] = (accumulate ? sums[2 * s] : 0) + sa[0];
+    sums[2 * s + 1] = (accumulate ? sums[2 * s + 1] : 0) + sb[0];
   }
 }
 
@@ -1640,8 +1649,12 @@ int WebRtcNsB200_SynthPcmDevice(int16_t* dst, size_t stride, int n_streams, uint
                                 uint32_t first_sample, uint32_t n_samples, uint32_t seed, void* st) {
   std::lock_guard<std::mutex> lk(g_mu);
   if ((stride & 1) || (n_samples & 1)) return Fail("stride and n_samples must be even");
-  synth_kernel<<<148 * 8, 256, 0, (cudaStream_t)st>>>(dst, stride, n_streams, first_stream, fs, first_sample,
-                                                     n_samples, seed);
+  if (n_streams <= 0 || n_samples == 0) return 0;
+  unsigned gx = (n_samples / 2 + 255) / 256;
+  if (gx > 32) gx = 32;
+  const dim3 grid(gx, n_streams < 65535 ? n_streams : 65535);
+  synth_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(dst, stride, n_streams, first_stream, fs, first_sample,
+                                                   n_samples, seed);
   ++g_launches;
   CU_OK(cudaGetLastError());
   return 0;
@@ -1653,7 +1666,15 @@ void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint3
 int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
                                 int64_t* sums, void* st) {
   std::lock_guard<std::mutex> lk(g_mu);
-  checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums);
+  checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 0);
+  ++g_launches;
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+int WebRtcNsB200_ChecksumAccumulateDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
+                                          int64_t* sums, void* st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 1);
   ++g_launches;
   CU_OK(cudaGetLastError());
   return 0;

@@ -198,3 +198,57 @@ def synth_pcm_host(n_streams, fs, n_samples, base_seed=1234, first_stream=0, fir
     for s in range(n_streams):
         lib.WebRtcNsB200_SynthPcmHost(_ptr(out[s]), first_stream + s, fs, first_sample, n_samples, base_seed)
     return out
+
+
+def run_generated_job(batch, frames, frames_per_launch, first_stream=0, base_seed=1234, sample=(), stream=None,
+                      on_launch=None):
+    """A job too large to hold as PCM (BASELINE config 5: 65 536 streams x 10 min): per
+    chunk of `frames_per_launch` frames the synthetic PCM of every stream of `batch` is generated on the
+    device, processed, and reduced to a running per-stream (sum, energy) checksum; input and output of
+    the streams listed in `sample` are also kept (host arrays) for comparison with the reference.
+    Everything is enqueued on one CUDA stream.  Returns (sums int64 [n, 2] numpy, {s: (in, out)}).
+    on_launch(i, ev_before, ev_after): optional hook receiving CUDA events around each process call."""
+    import torch
+    lib = batch._lib
+    n, fs = batch.n, batch.fs
+    fl = frame_len(fs)
+    F = int(frames_per_launch)
+    st = stream or torch.cuda.Stream()
+    bufs = [(torch.empty((n, F * fl), dtype=torch.int16, device="cuda"),
+             torch.empty((n, F * fl), dtype=torch.int16, device="cuda")) for _ in range(2)]
+    sums = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+    sample = list(sample)
+    idx = torch.tensor(sample, dtype=torch.long, device="cuda") if sample else None
+    keep_in = torch.empty((len(sample), frames * fl), dtype=torch.int16, device="cuda") if sample else None
+    keep_out = torch.empty_like(keep_in) if sample else None
+    with torch.cuda.stream(st):
+        i = 0
+        for f0 in range(0, frames, F):
+            nf = min(F, frames - f0)
+            x, y = bufs[i % 2]
+            rc = lib.WebRtcNsB200_SynthPcmDevice(C.c_void_p(x.data_ptr()), F * fl, n, first_stream, fs, f0 * fl,
+                                                 nf * fl, base_seed, C.c_void_p(st.cuda_stream))
+            if rc != 0:
+                raise _err(lib, "WebRtcNsB200_SynthPcmDevice")
+            ev = None
+            if on_launch is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record(st)
+            batch.process_device(x.data_ptr(), F * fl, y.data_ptr(), F * fl, nf, st.cuda_stream)
+            if ev is not None:
+                ev[1].record(st)
+                on_launch(i, ev[0], ev[1])
+            rc = lib.WebRtcNsB200_ChecksumAccumulateDevice(C.c_void_p(y.data_ptr()), F * fl, n, nf * fl,
+                                                           C.c_void_p(sums.data_ptr()), C.c_void_p(st.cuda_stream))
+            if rc != 0:
+                raise _err(lib, "WebRtcNsB200_ChecksumAccumulateDevice")
+            if sample:
+                keep_in[:, f0 * fl:(f0 + nf) * fl] = x[idx, :nf * fl]
+                keep_out[:, f0 * fl:(f0 + nf) * fl] = y[idx, :nf * fl]
+            i += 1
+    st.synchronize()
+    out = {}
+    if sample:
+        ki, ko = keep_in.cpu().numpy(), keep_out.cpu().numpy()
+        out = {s: (ki[j], ko[j]) for j, s in enumerate(sample)}
+    return sums.cpu().numpy(), out

@@ -147,6 +147,82 @@ def cpu_reference_run(kind, fs, mode, streams, frames, threads):
     return streams * frames * 0.01 / sec
 
 
+def config5(a, pkg, lib, torch, dist, rank, local_rank, world, barrier):
+    """BASELINE configs[4] / SURVEY.md 8d(5): --total-streams streams x --seconds at 16 kHz, each rank owning a
+    contiguous slice; PCM generated on the device per chunk of F frames, output reduced on the device to a
+    per-stream (sum, energy) checksum.  A step is one chunk (generate + process + reduce) of every stream of
+    the rank; the timed region is the whole job unless --steps cuts it short (explicit --steps only)."""
+    import numpy as np
+    from audiosignalprocess_b200.shard import shard_range
+    F = a.frames_per_step
+    lo, hi = shard_range(a.total_streams, world, rank)
+    n = hi - lo
+    frames = a.seconds * 100
+    if "--steps" in sys.argv:
+        frames = min(frames, a.steps * F)
+    steps = -(-frames // F)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    batch = pkg.NsBatch(n, a.fs, a.mode, fixed=a.fixed, devices=[local_rank])
+    pkg.run_generated_job(batch, max(1, a.warmup) * F, F, first_stream=lo, stream=stream)
+    batch.reset(a.mode)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.WebRtcNsB200_KernelLaunches()
+    pairs = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sums, _ = pkg.run_generated_job(batch, frames, F, first_stream=lo, stream=stream,
+                                    on_launch=lambda i, x, y: pairs.append((x, y)))
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = lib.WebRtcNsB200_KernelLaunches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    ms_proc = sum(x.elapsed_time(y) for x, y in pairs)
+    t = torch.tensor([ms_total, ms_proc], dtype=torch.float64, device=dev)
+    # a checksum of the per-stream checksums, summed over the ranks: the job's fingerprint
+    fp = torch.tensor([int(np.bitwise_xor.reduce(sums[:, 0] * 1000003 + sums[:, 1])) & 0x7fffffffffff, int(sums[:, 1].sum() >> 20)],
+                      dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fp, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        kind = "fixed" if a.fixed else "float"
+        peak, which = measured_peak_gbs()
+        audio_s = a.total_streams * frames * 0.01
+        ms_max, ms_proc_max = float(t[0].item()), float(t[1].item())
+        bytes_per_sf = algorithmic_bytes(kind, a.fs, F)
+        avg_launch_ms = ms_proc / len(pairs)
+        achieved = bytes_per_sf * n * F / (avg_launch_ms * 1e-3) / 1e9
+        line = {"metric": "ns_audio_seconds_per_second", "value": audio_s / (ms_max * 1e-3), "unit": "audio-s/s",
+                "n_gpus": world, "steps": steps, "warmup": max(1, a.warmup), "ms_per_step": ms_max / steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int16/int32" if a.fixed else "f32", "data": "synthetic",
+                "config": {"workload": "config 5: %d streams x %d s at %d Hz sharded over %d GPU(s) (%d per GPU), %s policy %d, "
+                                       "PCM generated on the device per chunk of F=%d frames, output reduced to per-stream checksums"
+                                       % (a.total_streams, frames // 100, a.fs, world, n, "WebRtcNsx fixed" if a.fixed else "WebRtcNs float",
+                                          a.mode, F),
+                           "streams_per_gpu": n, "fs": a.fs, "policy": a.mode, "frames_per_launch": F, "pcm": "int16",
+                           "l2": "every step generates and processes fresh PCM (in+out %.0f MB per step) larger than the 126 MB L2"
+                                 % (2 * n * F * (a.fs // 100) * 2 / 1e6)},
+                "clocks": sampler.summary(), "e2e": None, "gpu_launches": int(launches),
+                "process_only_value": audio_s / (ms_proc_max * 1e-3),
+                "job_fingerprint": [int(fp[0].item()), int(fp[1].item())],
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": which,
+                             "kernel": "nsx_process_kernel" if a.fixed else "nsf_process_kernel",
+                             "bytes_per_stream_frame": bytes_per_sf, "frames_per_launch": F, "launch_ms_avg": avg_launch_ms},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +234,11 @@ def main():
     ap.add_argument("--mode", type=int, default=2)
     ap.add_argument("--fixed", action="store_true", help="WebRtcNsx (fixed point) instead of float NS")
     ap.add_argument("--frames-per-step", type=int, default=100)
+    ap.add_argument("--config5", action="store_true",
+                    help="BASELINE configs[4]: --total-streams x --seconds of 16 kHz PCM generated on the device chunk "
+                         "by chunk, sharded over the ranks, output reduced to per-stream checksums (strong scaling)")
+    ap.add_argument("--total-streams", type=int, default=65536)
+    ap.add_argument("--seconds", type=int, default=600)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -219,6 +300,9 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if a.config5:
+        return config5(a, pkg, lib, torch, dist, rank, local_rank, world, barrier)
 
     total_steps = a.warmup + a.steps
     n_samples = total_steps * F * fl

@@ -166,6 +166,10 @@ void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint3
  * sums: [n_streams][2] int64 on the device. */
 int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams,
                                 uint32_t n_samples, int64_t* sums, void* cuda_stream);
+/* Same, added onto the sums already there: a job cut into chunks (config 5 generates, processes
+ * and reduces 10 minutes of PCM chunk by chunk) keeps one running checksum per stream. */
+int WebRtcNsB200_ChecksumAccumulateDevice(const int16_t* pcm, size_t stride, int n_streams,
+                                          uint32_t n_samples, int64_t* sums, void* cuda_stream);
 
 /* ---- 5. stream state snapshot / restore / migration --------------------------- */
 /* No reference counterpart (the reference's state is a malloc'ed struct the caller could memcpy:

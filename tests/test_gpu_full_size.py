@@ -91,3 +91,33 @@ def test_config4_48k_2048_streams(nslib, reflib):
         _, refi, _ = reflib.ns(fs, mode, xin)
         res.append(judge_float(refi.astype(np.float32), yout.astype(np.float32), slack=1.0))
     summarize_parity(res, "config 4 full size", 0.6)
+
+
+@pytest.mark.timeout(1200)
+def test_config5_shard_8192_streams_600s(nslib, reflib):
+    """configs[4]: 65 536 streams x 10 min at 16 kHz, sharded 8192 per GPU on 8 B200 -- one GPU's shard
+    at full length (8192 x 60 000 frames = 4.9e8 stream-frames).  1.26 TB of PCM each way in the whole
+    job, so the PCM is generated on the device chunk by chunk and the output reduced to a running
+    per-stream (sum, energy) checksum; sampled streams are kept and checked against the
+    compiled reference over the whole 10 minutes, and the checksums of ALL streams must not depend on
+    how the 60 000 frames are cut into launches (state carried through 600 launches == through 80)."""
+    n, fs, mode, frames = 8192, 16000, 2, 60000
+    first = 5 * 8192                       # the shard of rank 5 of 8: global stream indices
+    sample = [0, 3, 4102, 8191]
+    b = nslib.NsBatch(n, fs, mode, devices=[0])
+    sums_a, out = nslib.run_generated_job(b, frames, 100, first_stream=first, sample=sample)
+    res = []
+    for s in sample:
+        xin, yout = out[s]
+        assert np.array_equal(xin, nslib.synth_pcm_host(1, fs, frames * (fs // 100), first_stream=first + s)[0])
+        _, refi, _ = reflib.ns(fs, mode, xin)
+        res.append(judge_float(refi.astype(np.float32), yout.astype(np.float32), slack=1.0))
+        # the kept output is what the checksum saw
+        y64 = yout.astype(np.int64)
+        assert sums_a[s, 0] == y64.sum() and sums_a[s, 1] == (y64 * y64).sum()
+    summarize_parity(res, "config 5 shard, 10 min", 0.5)
+    b.reset(mode)
+    sums_b, _ = nslib.run_generated_job(b, frames, 750, first_stream=first)
+    b.close()
+    assert np.array_equal(sums_a, sums_b)
+    assert len(np.unique(sums_a[:, 1])) > n // 2
