@@ -24,6 +24,9 @@ SYMBOLS = {
     "WebRtcNsx_Process": (None, [_H, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     "WebRtcNs_ProcessBatch": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "WebRtcNsx_ProcessBatch": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "WebRtcNs_ProcessBatchAsync": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]),
+    "WebRtcNsx_ProcessBatchAsync": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]),
+    "WebRtcNsB200_WaitBatch": (C.c_int, [C.c_uint64]),
     "WebRtcNs_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNsx_ProcessBatchDevice": (C.c_int, [_HP, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "WebRtcNs_ProcessBatchBandsF32": (C.c_int, [_HP, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),

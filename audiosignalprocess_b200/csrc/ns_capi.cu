@@ -95,6 +95,14 @@ struct DeviceCtx {
   int32_t* d_down_sched = nullptr;     // 48 kHz: resampler schedule of the current launch
   size_t down_sched_words = 0;
   std::vector<cudaEvent_t> events;     // host-pointer batch pipeline (reused across calls)
+  // staging-buffer hand-over that survives the call (asynchronous batches form one pipeline):
+  // buffer b was last read by the kernel before pipe_kdone[b] and drained before pipe_drained[b]
+  cudaEvent_t pipe_kdone[8] = {}, pipe_drained[8] = {};
+  bool pipe_used[8] = {};
+  int pipe_bufs = 0;
+  size_t pipe_per = 0;                 // staging layout of the pipeline: samples per stream per buffer,
+  int pipe_count = 0;                  //   streams per buffer
+  unsigned long long pipe_seq = 0;     // chunks issued so far (buffer = seq % 3)
   // 32/48 kHz: one CUDA stream per pipeline stage, events between the stages of a chunk
   cudaStream_t stage_stream[9] = {};
   cudaEvent_t fork_event = nullptr;
@@ -102,6 +110,35 @@ struct DeviceCtx {
 };
 
 std::vector<DeviceCtx> g_devs;
+
+// Asynchronous host-pointer batches (WebRtcNs[x]_ProcessBatchAsync) still in flight: ticket ->
+// one completion event per device.  Every other entry point drains them first (ApiLock), so the
+// rest of the library keeps its "nothing of mine is running" assumption.
+struct PendingBatch {
+  uint64_t ticket;
+  std::vector<std::pair<int, cudaEvent_t>> done;
+};
+std::vector<PendingBatch> g_pending;
+uint64_t g_next_ticket = 1;
+
+void FinishPending(PendingBatch& p) {
+  for (auto& de : p.done) {
+    cudaSetDevice(de.first);
+    cudaEventSynchronize(de.second);
+    cudaEventDestroy(de.second);
+  }
+  p.done.clear();
+}
+void DrainPendingLocked() {
+  for (PendingBatch& p : g_pending) FinishPending(p);
+  g_pending.clear();
+}
+struct ApiLock {
+  std::lock_guard<std::mutex> guard;
+  explicit ApiLock(bool drain = true) : guard(g_mu) {
+    if (drain && !g_pending.empty()) DrainPendingLocked();
+  }
+};
 
 int EnsureDevices() {
   if (!g_devs.empty()) return 0;
@@ -245,7 +282,7 @@ int UploadSlots(DeviceCtx& d, const std::vector<int>& slots, cudaStream_t st) {
 }
 
 int Create(void** out, uint32_t magic) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (!out) return Fail("NULL handle pointer");
   *out = nullptr;
   int dev = g_create_device;
@@ -280,7 +317,7 @@ int Create(void** out, uint32_t magic) {
 }
 
 int Free(void* hv, uint32_t magic) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AsHandle(hv, magic);
   if (!h) return 0;  // reference: free(NULL) is fine, returns 0
   DeviceCtx& d = g_devs[h->dev];
@@ -298,7 +335,7 @@ int Free(void* hv, uint32_t magic) {
 int BandSlot(const Handle* h) { return h->magic == kMagicF ? 2 * h->slot : 2 * h->slot + 1; }
 
 int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (!hv || n <= 0) return Fail("no handles");
   if (!(fs == 8000 || fs == 16000 || fs == 32000 || fs == 48000)) return Fail("unsupported fs");
   if (mode < 0 || mode > 3) return Fail("mode out of range");
@@ -374,7 +411,7 @@ int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
 int SetPolicy(void* hv, int mode, uint32_t magic) {
   Handle* h;
   {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiLock lk;
     h = AsHandle(hv, magic);
     if (!h) return Fail("bad handle");
     if (mode < 0 || mode > 3) return Fail("mode out of range");
@@ -782,7 +819,7 @@ int CheckBatch(void* const* hv, int n, uint32_t magic, size_t in_stride, size_t 
 
 int BatchDevice(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
                 int16_t* out, size_t out_stride, int frames, void* stream) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   std::vector<Handle*> hs;
   if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
   if (frames == 0) return 0;
@@ -798,8 +835,11 @@ int BatchDevice(void* const* hv, int n, uint32_t magic, const int16_t* in, size_
 // Frames are cut into chunks so that the H2D copy of chunk c+1 and the D2H copy
 // of chunk c-1 overlap the kernel of chunk c (three streams, events).
 int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
-              int16_t* out, size_t out_stride, int frames) {
-  std::lock_guard<std::mutex> lk(g_mu);
+              int16_t* out, size_t out_stride, int frames, uint64_t* ticket = nullptr) {
+  // ticket: asynchronous call -- everything is enqueued behind what earlier asynchronous calls
+  // left in the three queues and the call returns without waiting (0 = nothing to wait for)
+  ApiLock lk(ticket == nullptr);
+  if (ticket) *ticket = 0;
   std::vector<Handle*> hs;
   if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
   if (frames == 0) return 0;
@@ -812,6 +852,8 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     else runs.push_back(Run{hs[i]->dev, i, 1});
   }
   if (NumBands(hs[0]->fs) > 1) {
+    // (asynchronous calls: this path blocks, after whatever is still in flight)
+    if (ticket && !g_pending.empty()) DrainPendingLocked();
     // 32/48 kHz: the copies are the first and last stage of the band pipeline (RunBandBlock);
     // staging holds one block of frames per direction
     const int block = frames < kBandBlockFrames ? frames : kBandBlockFrames;
@@ -853,8 +895,10 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   {
     const double bytes_per_frame = (double)n * fl * sizeof(int16_t);
     // ~12 MB per chunk, but at least four chunks when the call is big enough for 1.5 MB chunks
-    double target = 12.0e6;
-    if (bytes_per_frame * frames / 4.0 < target) target = bytes_per_frame * frames / 4.0;
+    // (asynchronous calls queue behind each other, so fill and drain are paid once per stream of
+    // calls, not per call: ~32 MB chunks measured best, tools/e2e_sweep.sh)
+    double target = ticket ? 32.0e6 : 12.0e6;
+    if (!ticket && bytes_per_frame * frames / 4.0 < target) target = bytes_per_frame * frames / 4.0;
     if (target < 1.5e6) target = 1.5e6;
     int c = (int)(target / bytes_per_frame + 0.5);
     if (c < 1) c = 1;
@@ -869,7 +913,7 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   // drain (last kernel + last copy-out), which nothing overlaps
   std::vector<int> starts;   // first frame of each chunk, plus the end
   {
-    const int edge = chunk >= 4 && frames >= 3 * chunk ? chunk / 2 : chunk;
+    const int edge = !ticket && chunk >= 4 && frames >= 3 * chunk ? chunk / 2 : chunk;
     int f0 = 0;
     starts.push_back(0);
     f0 += edge < frames ? edge : frames;
@@ -881,7 +925,11 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     starts.push_back(frames);
   }
   const int nchunks = (int)starts.size() - 1;
-  constexpr int kBuf = 3;   // staging buffers per direction
+  int kBuf = 3;   // staging buffers per direction
+  if (const char* e = getenv("NSB200_STAGE_BUFS")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 8) kBuf = v;
+  }
   for (const Run& r : runs) {
     DeviceCtx* d;
     if (DeviceReady(r.dev, &d) != 0) return -1;
@@ -893,7 +941,23 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
       CU_OK(cudaMalloc(&d->d_in, sizeof(int16_t) * need));
       CU_OK(cudaMalloc(&d->d_out, sizeof(int16_t) * need));
       d->stage_elems = need;
+      d->pipe_per = 0;
     }
+    if (d->pipe_per != per || d->pipe_count != r.count || d->pipe_bufs != kBuf) {
+      // the buffers are cut differently from the pipeline still in flight: let it run dry
+      CU_OK(cudaStreamSynchronize(d->copy_in));
+      CU_OK(cudaStreamSynchronize(d->stream));
+      CU_OK(cudaStreamSynchronize(d->copy_out));
+      d->pipe_per = per;
+      d->pipe_count = r.count;
+      d->pipe_bufs = kBuf;
+      for (int b = 0; b < kBuf; ++b) d->pipe_used[b] = false;
+    }
+    for (int b = 0; b < kBuf; ++b)
+      if (!d->pipe_kdone[b]) {
+        CU_OK(cudaEventCreateWithFlags(&d->pipe_kdone[b], cudaEventDisableTiming));
+        CU_OK(cudaEventCreateWithFlags(&d->pipe_drained[b], cudaEventDisableTiming));
+      }
     const size_t nev = 3 * (size_t)nchunks;
     while (d->events.size() < nev) {
       cudaEvent_t e;
@@ -923,12 +987,14 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     for (int c = 0; c < nchunks; ++c) {
       const int f0 = starts[c];
       const int nf = starts[c + 1] - f0;
-      int16_t* din = d->d_in + (size_t)(c % kBuf) * r.count * per;
-      int16_t* dout = d->d_out + (size_t)(c % kBuf) * r.count * per;
-      // buffer c % kBuf was last read by kernel c-kBuf and last drained by copy-out c-kBuf
-      if (c >= kBuf) {
-        CU_OK(cudaStreamWaitEvent(d->copy_in, ev[3 * (c - kBuf) + 1], 0));
-        CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * (c - kBuf) + 2], 0));
+      const int b = (int)((d->pipe_seq + (unsigned long long)c) % (unsigned long long)kBuf);
+      int16_t* din = d->d_in + (size_t)b * r.count * per;
+      int16_t* dout = d->d_out + (size_t)b * r.count * per;
+      // buffer b was last read by the kernel three chunks back and last drained by its copy-out
+      // (of this call or, for asynchronous calls, of the one before)
+      if (d->pipe_used[b]) {
+        CU_OK(cudaStreamWaitEvent(d->copy_in, d->pipe_kdone[b], 0));
+        CU_OK(cudaStreamWaitEvent(d->stream, d->pipe_drained[b], 0));
       }
       mark(d->copy_in);
       CU_OK(cudaMemcpy2DAsync(din, per * sizeof(int16_t), in + (size_t)r.first * in_stride + (size_t)f0 * fl,
@@ -940,15 +1006,17 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
       mark(d->stream);
       if (RunDevice(*d, magic, sub, din, per, dout, per, nf, d->stream) != 0) return -1;
       mark(d->stream);
-      CU_OK(cudaEventRecord(ev[3 * c + 1], d->stream));
-      CU_OK(cudaStreamWaitEvent(d->copy_out, ev[3 * c + 1], 0));
+      CU_OK(cudaEventRecord(d->pipe_kdone[b], d->stream));
+      CU_OK(cudaStreamWaitEvent(d->copy_out, d->pipe_kdone[b], 0));
       mark(d->copy_out);
       CU_OK(cudaMemcpy2DAsync(out + (size_t)r.first * out_stride + (size_t)f0 * fl,
                               out_stride * sizeof(int16_t), dout, per * sizeof(int16_t),
                               (size_t)nf * fl * sizeof(int16_t), r.count, cudaMemcpyDeviceToHost, d->copy_out));
       mark(d->copy_out);
-      CU_OK(cudaEventRecord(ev[3 * c + 2], d->copy_out));
+      CU_OK(cudaEventRecord(d->pipe_drained[b], d->copy_out));
+      d->pipe_used[b] = true;
     }
+    d->pipe_seq += (unsigned long long)nchunks;
     if (trace) {
       CU_OK(cudaDeviceSynchronize());
       for (int c = 0; c < nchunks; ++c) {
@@ -959,6 +1027,22 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
       for (auto e : tev) cudaEventDestroy(e);
     }
   }
+  if (ticket) {
+    // completion = the last copy-out of every device (the copy-out queue is in order)
+    PendingBatch pb;
+    pb.ticket = g_next_ticket++;
+    for (size_t ri = 0; ri < runs.size(); ++ri) {
+      DeviceCtx* d = &g_devs[runs[ri].dev];
+      CU_OK(cudaSetDevice(runs[ri].dev));
+      cudaEvent_t e;
+      CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU_OK(cudaEventRecord(e, d->copy_out));
+      pb.done.push_back(std::make_pair(runs[ri].dev, e));
+    }
+    *ticket = pb.ticket;
+    g_pending.push_back(pb);
+    return 0;
+  }
   for (size_t ri = 0; ri < runs.size(); ++ri) {
     DeviceCtx* d = &g_devs[runs[ri].dev];
     CU_OK(cudaSetDevice(runs[ri].dev));
@@ -968,11 +1052,25 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   return 0;
 }
 
+int WaitBatch(uint64_t ticket) {
+  ApiLock lk(false);
+  // tickets complete in issue order per device, but callers may wait in any order
+  for (size_t i = 0; i < g_pending.size(); ++i)
+    if (g_pending[i].ticket == ticket) {
+      FinishPending(g_pending[i]);
+      g_pending.erase(g_pending.begin() + (long)i);
+      break;
+    }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return Fail(std::string("asynchronous batch failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 // Single-stream float call = batch of one over float band frames.
 // ana (optional): [stream][frame][frame_len] band-0 frames for Analyze, stride ana_ss floats.
 int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_ss, float* out,
                     size_t out_ss, int frames, const float* ana = nullptr, size_t ana_ss = 0) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (!hv || n <= 0) return Fail("no handles");
   if (nb < 1 || nb > 3) return Fail("num_bands out of range");
   std::vector<Handle*> hs(n);
@@ -1041,7 +1139,7 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
 // Full-band int16 PCM with a separate Analyze signal, host pointers (8/16 kHz, float NS).
 int SplitBatchHost(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
                    int16_t* out, size_t out_stride, int frames) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   std::vector<Handle*> hs;
   if (!ana) return Fail("NULL Analyze signal");
   if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
@@ -1072,7 +1170,7 @@ int SplitBatchHost(void* const* hv, int n, const int16_t* ana, size_t ana_stride
 }
 int SplitBatchDevice(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
                      int16_t* out, size_t out_stride, int frames, void* stream) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   std::vector<Handle*> hs;
   if (!ana) return Fail("NULL Analyze signal");
   if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
@@ -1242,7 +1340,7 @@ __global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams
 // (+S16ToFloat) -> D2H, in place (apm_ns.cpp:47-132 does the same per 10 ms on the host).
 template <typename T>
 int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_channel) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (!data) return Fail("NULL data");
   std::vector<Handle*> hs;
   if (CheckBatch(hv, channels, kMagicF, 0, 0, 0, &hs) != 0) return -1;
@@ -1323,14 +1421,14 @@ SlabRefs SlabsOf(DeviceCtx& d, const Handle* h, int slot) {
   return r;
 }
 size_t StateSize(const void* hv) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return 0;
   SlabRefs r = SlabsOf(g_devs[h->dev], h, h->slot);
   return sizeof(StateBlobHeader) + r.bytes[0] + r.bytes[1] + r.bytes[2];
 }
 int ExportState(const void* hv, void* buf, size_t size) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
   if (!buf) return Fail("NULL buffer");
@@ -1363,7 +1461,7 @@ int ExportState(const void* hv, void* buf, size_t size) {
   return 0;
 }
 int ImportState(void* hv, const void* buf, size_t size) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
   if (!buf || size < sizeof(StateBlobHeader)) return Fail("state blob too small");
@@ -1395,7 +1493,7 @@ int ImportState(void* hv, const void* buf, size_t size) {
 // Moves a stream to another GPU: new slot there, slabs copied device to device (NVLink peer copy
 // when the GPUs are peers, staged by the driver otherwise), old slot released.
 int MigrateHandle(void* hv, int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
   if (EnsureDevices() != 0) return -1;
@@ -1438,7 +1536,7 @@ int WebRtcNs_Init(NsHandle* h, uint32_t fs) {
 int WebRtcNs_set_policy(NsHandle* h, int mode) { return SetPolicy(h, mode, kMagicF); }
 
 void WebRtcNs_Analyze(NsHandle* hv, const float* spframe) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag || !spframe) {
     Fail("WebRtcNs_Analyze: handle not initialised");
@@ -1451,7 +1549,7 @@ void WebRtcNs_Analyze(NsHandle* hv, const float* spframe) {
 void WebRtcNs_Process(NsHandle* hv, const float* const* spframe, int num_bands, float* const* outframe) {
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag || !spframe || !outframe || num_bands < 1 || num_bands > 3) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiLock lk;
     Fail("WebRtcNs_Process: handle not initialised or bad arguments");
     return;
   }
@@ -1471,7 +1569,7 @@ void WebRtcNs_Process(NsHandle* hv, const float* const* spframe, int num_bands, 
 }
 
 float WebRtcNs_prior_speech_probability(NsHandle* hv) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag) return -1.f;
   DeviceCtx* d;
@@ -1495,11 +1593,11 @@ int WebRtcNsx_set_policy(NsxHandle* h, int mode) { return SetPolicy(h, mode, kMa
 void WebRtcNsx_Process(NsxHandle* hv, const short* const* speechFrame, int num_bands, short* const* outFrame) {
   Handle* h = AsHandle(hv, kMagicX);
   if (!h || !h->init_flag || !speechFrame || !outFrame || num_bands < 1 || num_bands > 3) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiLock lk;
     Fail("WebRtcNsx_Process: handle not initialised or bad arguments");
     return;
   }
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   const int fl = h->fs == 8000 ? 80 : 160;
   const int ana = h->fs == 8000 ? 128 : 256;
   DeviceCtx* d;
@@ -1539,6 +1637,17 @@ int WebRtcNs_ProcessBatch(NsHandle* const* hs, int n, const int16_t* in, size_t 
 int WebRtcNsx_ProcessBatch(NsxHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os, int frames) {
   return BatchHost(reinterpret_cast<void* const*>(hs), n, kMagicX, in, is, out, os, frames);
 }
+int WebRtcNs_ProcessBatchAsync(NsHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os, int frames,
+                               uint64_t* ticket) {
+  if (!ticket) return Fail("NULL ticket pointer");
+  return BatchHost(reinterpret_cast<void* const*>(hs), n, kMagicF, in, is, out, os, frames, ticket);
+}
+int WebRtcNsx_ProcessBatchAsync(NsxHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os, int frames,
+                                uint64_t* ticket) {
+  if (!ticket) return Fail("NULL ticket pointer");
+  return BatchHost(reinterpret_cast<void* const*>(hs), n, kMagicX, in, is, out, os, frames, ticket);
+}
+int WebRtcNsB200_WaitBatch(uint64_t ticket) { return WaitBatch(ticket); }
 int WebRtcNs_ProcessBatchDevice(NsHandle* const* hs, int n, const int16_t* in, size_t is, int16_t* out, size_t os,
                                 int frames, void* st) {
   return BatchDevice(reinterpret_cast<void* const*>(hs), n, kMagicF, in, is, out, os, frames, st);
@@ -1562,7 +1671,7 @@ int WebRtcNs_AnalyzeProcessBatchDevice(NsHandle* const* hs, int n, const int16_t
 int WebRtcNs_AnalyzeProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* ana, size_t as, const float* in,
                                          size_t is, float* out, size_t os, int frames) {
   if (!ana) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    ApiLock lk;
     return Fail("NULL Analyze signal");
   }
   return ProcessBandsF32((void* const*)hs, n, nb, in, is, out, os, frames, ana, as);
@@ -1585,13 +1694,13 @@ int WebRtcNsB200_ExportState(const void* handle, void* buf, size_t size) { retur
 int WebRtcNsB200_ImportState(void* handle, const void* buf, size_t size) { return ImportState(handle, buf, size); }
 int WebRtcNsB200_MigrateHandle(void* handle, int device) { return MigrateHandle(handle, device); }
 int WebRtcNsB200_HandleDevice(const void* handle) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   Handle* h = AnyHandle(handle);
   return h ? h->dev : -1;
 }
 
 int WebRtcNsB200_SetCreateDevice(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (device >= 0) {
     if (EnsureDevices() != 0) return -1;
     if (device >= (int)g_devs.size()) return Fail("bad device index");
@@ -1600,12 +1709,12 @@ int WebRtcNsB200_SetCreateDevice(int device) {
   return 0;
 }
 int WebRtcNsB200_DeviceCount(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if (EnsureDevices() != 0) return 0;
   return (int)g_devs.size();
 }
 int WebRtcNsB200_Synchronize(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   for (auto& d : g_devs) {
     if (!d.ready) continue;
     CU_OK(cudaSetDevice(d.dev));
@@ -1617,7 +1726,7 @@ const char* WebRtcNsB200_LastError(void) { return g_err.c_str(); }
 uint64_t WebRtcNsB200_KernelLaunches(void) { return g_launches; }
 
 int WebRtcNsB200_SelfTestStats(uint64_t n_cases, uint64_t* stats) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   int dev = 0;
   if (EnsureDevices() != 0) return -1;
   cudaGetDevice(&dev);
@@ -1647,7 +1756,7 @@ int WebRtcNsB200_SelfTest(uint64_t n_cases) {
 
 int WebRtcNsB200_SynthPcmDevice(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream, uint32_t fs,
                                 uint32_t first_sample, uint32_t n_samples, uint32_t seed, void* st) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   if ((stride & 1) || (n_samples & 1)) return Fail("stride and n_samples must be even");
   if (n_streams <= 0 || n_samples == 0) return 0;
   unsigned gx = (n_samples / 2 + 255) / 256;
@@ -1665,7 +1774,7 @@ void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint3
 }
 int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
                                 int64_t* sums, void* st) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 0);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -1673,7 +1782,7 @@ int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams
 }
 int WebRtcNsB200_ChecksumAccumulateDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
                                           int64_t* sums, void* st) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  ApiLock lk;
   checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 1);
   ++g_launches;
   CU_OK(cudaGetLastError());

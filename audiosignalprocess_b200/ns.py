@@ -153,6 +153,20 @@ class NsBatch:
         if rc != 0:
             raise _err(self._lib, self._p + "_ProcessBatch")
 
+    def process_ptr_async(self, in_ptr, in_stride, out_ptr, out_stride, frames):
+        """Page-locked host pointers; returns a ticket at once (WebRtcNs[x]_ProcessBatchAsync).  The
+        buffers belong to the library until wait(ticket)."""
+        t = C.c_uint64(0)
+        rc = getattr(self._lib, self._p + "_ProcessBatchAsync")(
+            self._handles, self.n, C.c_void_p(in_ptr), in_stride, C.c_void_p(out_ptr), out_stride, frames, C.byref(t))
+        if rc != 0:
+            raise _err(self._lib, self._p + "_ProcessBatchAsync")
+        return t.value
+
+    def wait(self, ticket):
+        if self._lib.WebRtcNsB200_WaitBatch(C.c_uint64(ticket)) != 0:
+            raise _err(self._lib, "WebRtcNsB200_WaitBatch")
+
     def process_device(self, in_ptr, in_stride, out_ptr, out_stride, frames, stream=0):
         """Device pointers; enqueues on `stream` (cudaStream_t as int) and returns immediately."""
         rc = getattr(self._lib, self._p + "_ProcessBatchDevice")(

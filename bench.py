@@ -345,28 +345,58 @@ def main():
     audio_s = a.streams * a.steps * F * 0.01 * world
     value = audio_s / (ms_total_max * 1e-3)
 
-    # ---- end to end through the host-pointer C call, pinned buffers
+    # ---- end to end through the host-pointer C calls, pinned buffers.  Every step copies its input from
+    # pinned host memory and its result is read on the host.  Two forms of the same entry point:
+    #   blocking   one WebRtcNs_ProcessBatch per step (each call pays its own pipeline fill and drain)
+    #   streaming  WebRtcNs_ProcessBatchAsync with two steps in flight on two buffer pairs, a step's result
+    #              read after WebRtcNsB200_WaitBatch -- how a caller that streams audio uses the library
     e2e = None
     if not a.no_e2e:
         e_steps = a.steps
-        host_in = torch.empty((a.streams, F * fl), dtype=torch.int16).pin_memory()
-        host_out = torch.empty((a.streams, F * fl), dtype=torch.int16).pin_memory()
-        host_in.copy_(pcm_in[:, :F * fl].cpu())
-        batch.reset(a.mode)
-        for _ in range(a.warmup):
-            batch.process_ptr(host_in.data_ptr(), F * fl, host_out.data_ptr(), F * fl, F)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            batch.process_ptr(host_in.data_ptr(), F * fl, host_out.data_ptr(), F * fl, F)
-            _ = int(host_out[0, 0])   # the step's result is read on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": a.streams * e_steps * F * 0.01 * world / float(t.item()), "unit": "audio-s/s",
-               "h2d_bytes_per_step": a.streams * F * fl * 2, "d2h_bytes_per_step": a.streams * F * fl * 2}
+        n1 = F * fl
+        host_in = [torch.empty((a.streams, n1), dtype=torch.int16).pin_memory() for _ in range(2)]
+        host_out = [torch.empty((a.streams, n1), dtype=torch.int16).pin_memory() for _ in range(2)]
+        for k in range(2):
+            host_in[k].copy_(pcm_in[:, k * n1:(k + 1) * n1].cpu())
+
+        def timed(fn):
+            batch.reset(a.mode)
+            fn(a.warmup)
+            barrier()
+            t0 = time.perf_counter()
+            fn(e_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return a.streams * e_steps * F * 0.01 * world / float(tt.item())
+
+        def run_blocking(steps):
+            for i in range(steps):
+                k = i & 1
+                batch.process_ptr(host_in[k].data_ptr(), n1, host_out[k].data_ptr(), n1, F)
+                _ = int(host_out[k][0, 0])   # the step's result is read on the host
+
+        def run_streaming(steps):
+            tickets = [None, None]
+            for i in range(steps):
+                k = i & 1
+                if tickets[k] is not None:
+                    batch.wait(tickets[k])
+                    _ = int(host_out[k][0, 0])   # result of step i-2, read before its buffers are reused
+                tickets[k] = batch.process_ptr_async(host_in[k].data_ptr(), n1, host_out[k].data_ptr(), n1, F)
+            for k in ((steps & 1), 1 - (steps & 1)):
+                if tickets[k] is not None:
+                    batch.wait(tickets[k])
+                    _ = int(host_out[k][0, 0])
+
+        v_block = timed(run_blocking)
+        v_stream = timed(run_streaming)
+        e2e = {"value": v_stream, "unit": "audio-s/s",
+               "h2d_bytes_per_step": a.streams * n1 * 2, "d2h_bytes_per_step": a.streams * n1 * 2,
+               "api": "WebRtcNs%s_ProcessBatchAsync + WebRtcNsB200_WaitBatch, two steps in flight" % ("x" if a.fixed else ""),
+               "blocking_value": v_block, "blocking_api": "WebRtcNs%s_ProcessBatch, one call per step" % ("x" if a.fixed else "")}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

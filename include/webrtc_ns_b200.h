@@ -78,6 +78,24 @@ int WebRtcNs_ProcessBatch(NsHandle* const* handles, int n_streams, const int16_t
                           size_t in_stride, int16_t* pcm_out, size_t out_stride, int frames);
 int WebRtcNsx_ProcessBatch(NsxHandle* const* handles, int n_streams, const int16_t* pcm_in,
                            size_t in_stride, int16_t* pcm_out, size_t out_stride, int frames);
+/* Asynchronous form of WebRtcNs[x]_ProcessBatch for callers that stream: same arguments and
+ * results, but the call returns as soon as its copies and kernels are enqueued, and *ticket names
+ * it.  `in` must stay unchanged and `out` unread until WebRtcNsB200_WaitBatch(ticket) returns.
+ * Consecutive asynchronous calls form ONE pipeline over the GPU's two copy engines: the copy-out
+ * of call k overlaps the copy-in and kernels of call k+1, so a caller that keeps two calls in
+ * flight (two buffer pairs) is bound by PCIe duplex bandwidth, not by each call's fill and drain.
+ * Host buffers must be page-locked (cudaHostAlloc / cudaHostRegister) -- from pageable memory
+ * CUDA copies synchronously and the call degenerates to the blocking one.  Any other library
+ * call first waits for every batch still in flight, so mixing the two forms is safe.  At 32/48
+ * kHz the call blocks (ticket 0).  WaitBatch(0) and waiting twice are no-ops. */
+int WebRtcNs_ProcessBatchAsync(NsHandle* const* handles, int n_streams, const int16_t* pcm_in,
+                               size_t in_stride, int16_t* pcm_out, size_t out_stride, int frames,
+                               uint64_t* ticket);
+int WebRtcNsx_ProcessBatchAsync(NsxHandle* const* handles, int n_streams, const int16_t* pcm_in,
+                                size_t in_stride, int16_t* pcm_out, size_t out_stride, int frames,
+                                uint64_t* ticket);
+int WebRtcNsB200_WaitBatch(uint64_t ticket);
+
 /*
  * Device-pointer version: pcm_in/pcm_out are device memory on the GPU that owns
  * ALL the handles; the work is enqueued on cuda_stream (a cudaStream_t cast to
