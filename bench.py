@@ -260,8 +260,8 @@ def main():
         if rank != 0:
             return 0
         cores = os.cpu_count() or 1
-        # bounded sample of the same workload: cores*8 streams, F frames per step
-        streams = min(a.streams, cores * 8)
+        # bounded sample of the same workload: cores*32 streams, F frames per step (a few seconds in all)
+        streams = min(a.streams, cores * 32)
         for _ in range(min(a.warmup, 1)):
             cpu_reference_run(kind, a.fs, a.mode, streams, F, cores)
         t0 = time.time()
@@ -415,8 +415,9 @@ def main():
         cpu = None
         if not a.no_cpu:
             cores = os.cpu_count() or 1
+            # ~15-25 s of CPU work: 8 streams per core, 60 s of audio each (the configuration's duration)
             streams = cores * 8
-            frames = 1000
+            frames = 6000 if a.fs <= 16000 else 2000
             v = cpu_reference_run(kind, a.fs, a.mode, streams, frames, cores)
             if v is not None:
                 cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",

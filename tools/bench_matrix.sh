@@ -10,13 +10,10 @@ run --steps 30 --warmup 3 --fs 8000
 run --steps 20 --warmup 3 --fs 32000 --streams 2048 --frames-per-step 50
 run --steps 20 --warmup 3 --fs 48000 --streams 2048 --frames-per-step 50
 run --steps 20 --warmup 3 --fs 48000 --streams 2048 --frames-per-step 50 --fixed
-run --steps 200 --warmup 10 --frames-per-step 1 --no-cpu
-run --steps 100 --warmup 5 --frames-per-step 10 --no-cpu
-python - <<'PY' >> $O
-import json
-rows=[]
-lines=open("gpurun_out/%s_matrix.log" % "TAG").read().splitlines() if False else []
-PY
+run --steps 200 --warmup 10 --frames-per-step 1 --no-cpu --no-e2e
+run --steps 200 --warmup 10 --frames-per-step 1 --no-cpu --no-e2e --streams 32768
+run --steps 100 --warmup 5 --frames-per-step 10 --no-cpu --no-e2e
+run --config5 --total-streams 8192 --seconds 600
 python - "$O" <<'PY'
 import json,sys
 lines=open(sys.argv[1]).read().splitlines()
@@ -26,5 +23,7 @@ for i in range(0,len(lines)-1,2):
     except Exception: print(lines[i],"FAILED"); continue
     cb=d.get("cpu_baseline") or {}
     e=d.get("e2e") or {}
-    print("%-70s %8.3f ms/step  value %10.0f  e2e %10.0f  cpu %8.0f (%s cores)  frac %.4f" % (lines[i][3:], d["ms_per_step"], d["value"], e.get("value") or 0, cb.get("value") or 0, cb.get("cores"), d["roofline"]["frac"]))
+    print("%-72s %8.4f ms/step  value %10.0f  e2e %10.0f (blocking %10.0f)  cpu %8.0f (%s cores)  frac %.4f" % (
+        lines[i][3:], d["ms_per_step"], d["value"], e.get("value") or 0, e.get("blocking_value") or 0,
+        cb.get("value") or 0, cb.get("cores"), d["roofline"]["frac"]))
 PY
