@@ -50,6 +50,20 @@ def measured_traffic(kernel, frames_per_launch, streams):
     return None
 
 
+def measured_instructions(kernel, frames_per_launch, streams):
+    """Warp instructions per stream-frame of the dominant kernel from the committed ncu summary of the
+    same configuration, else None (for the issue-rate view of a kernel that is not HBM-bound)."""
+    tag = {"nsf_process_kernel": "nsf", "nsx_process_kernel": "nsx"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", "r1_%s_kernel_F%d.json" % (tag, frames_per_launch))
+    try:
+        d = json.load(open(path))
+        if d["units_per_launch"] == streams * frames_per_launch:
+            return d["warp_instructions_per_unit"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -412,6 +426,14 @@ def main():
                     "peak_source": which, "kernel": kname,
                     "bytes_per_stream_frame": bytes_per_sf, "frames_per_launch": F,
                     "launch_ms_avg": avg_ms, "launch_ms_median": med}
+        # The kernel is issue-bound at large F: the same launch time against one warp
+        # instruction per scheduler-cycle (4 schedulers x SMs x the SM clock sampled during the run).
+        wi = measured_instructions(kname, F, a.streams) if a.fs == 16000 else None
+        clk = sampler.summary().get("sm_mhz")
+        if wi and clk:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            roofline["issue"] = {"warp_instructions_per_stream_frame": wi, "source": "ncu summary under profiles/",
+                                 "frac_of_issue_peak": wi * a.streams * F / (avg_ms * 1e-3) / (4.0 * sms * clk * 1e6)}
         cpu = None
         if not a.no_cpu:
             cores = os.cpu_count() or 1
