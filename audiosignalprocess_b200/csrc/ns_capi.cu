@@ -84,6 +84,7 @@ struct DeviceCtx {
   int* h_slots = nullptr;       // pinned
   int slots_cap = 0;
   std::vector<int> cached_slots;
+  int slot_run = 0;             // cached_slots[i] == cached_slots[0] + i for i < slot_run
   // device staging for the host-pointer batch API
   int16_t* d_in = nullptr;
   int16_t* d_out = nullptr;
@@ -293,6 +294,11 @@ int UploadSlots(DeviceCtx& d, const std::vector<int>& slots, cudaStream_t st) {
   CU_OK(cudaMemcpyAsync(d.d_slots, d.h_slots, sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
   if (st != d.stream) CU_OK(cudaStreamSynchronize(d.stream));
   d.cached_slots = slots;
+  // handles created one after the other sit in consecutive slots: the kernel then computes the
+  // slot instead of loading it (one dependent global-memory latency less per warp)
+  int run = n > 0 ? 1 : 0;
+  while (run < n && slots[run] == slots[0] + run) ++run;
+  d.slot_run = run;
   return 0;
 }
 
@@ -568,7 +574,8 @@ int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t
     NsfLaunch p;
     p.state = (float*)d.f_state.base;
     p.hist = (int*)d.f_hist.base;
-    p.slots = d.d_slots;
+    p.slots = d.slot_run >= n ? nullptr : d.d_slots;
+    p.slot_base = d.slot_run >= n ? d.cached_slots[0] : 0;
     p.tables = d.d_nsf_tables;
     p.in = in + (size_t)f0 * fstride;
     p.out = out + (size_t)f0 * fstride;

@@ -57,6 +57,17 @@ inline void nsf_fill_tables(Tables* t) {
     t->sum_log_i[v] = s;
     t->sum_log_i_sq[v] = s2;
   }
+  // shared-memory images (nsf_layout.h); the regrouped twiddles follow ns_warp.cuh fft_fill_tw12
+  for (int v = 0; v < 2; ++v) {
+    float* img = t->img[v];
+    const int ana = v == 0 ? 256 : 128, nc = ana / 2, l = nc / 4, m = l / 4;
+    memcpy(img + kNsfImgWin, v == 0 ? t->win256 : t->win128, sizeof(float) * ana);
+    memcpy(img + kNsfImgTw, t->tw, sizeof(t->tw));
+    memcpy(img + kNsfImgLogi, t->logi, sizeof(t->logi));
+    float2* tw12 = reinterpret_cast<float2*>(img + kNsfImgTw12);
+    for (int i = 0; i < 96; ++i) tw12[i] = t->tw[((i & 31) * (i / 32 + 1) * (256 / nc)) & 255];
+    for (int i = 0; i < 24; ++i) tw12[96 + i] = t->tw[(((i & 7) % m) * (i / 8 + 1) * (256 / l)) & 255];
+  }
 }
 
 inline bool nsf_mode_params(int mode, float* overdrive, float* denoise_bound, int* gainmap) {

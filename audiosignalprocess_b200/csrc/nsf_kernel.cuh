@@ -42,7 +42,12 @@ constexpr int kNsfWarpsPerCta = NSF_WARPS_PER_CTA;
 #define NSF_CTAS_PER_SM 8
 #endif
 constexpr int kNsfCtasPerSm = NSF_CTAS_PER_SM;
-constexpr int kNsfCtaTableWords = 912 + 2 * kFftTw12F2;  // win 256 | tw 512 | logi 132 | pad | regrouped twiddles 240
+// Per-CTA shared memory: the table image (nsf_layout.h: win 256 | tw 512 | logi 132 | pad | regrouped
+// twiddles 240) followed by the mbarriers of the TMA bulk copies: one for the tables, two per warp
+// (header + sample histories | per-bin records).
+static_assert(kNsfImgTw12 + 2 * kFftTw12F2 == kNsfTableImgWords, "table image layout");
+constexpr int kNsfCtaBarWords = (2 * (1 + 2 * kNsfWarpsPerCta) + 3) / 4 * 4;
+constexpr int kNsfCtaTableWords = kNsfTableImgWords + kNsfCtaBarWords;
 // Per-warp shared memory (32-bit words): header x2 | bin records | FFT scratch | analysis block
 // (256) | synthesis overlap (96) | split: aux arrays + Process block (256) | high-band delay blocks.
 // The sample histories live in shared memory, not registers: the register budget of the per-bin
@@ -208,24 +213,17 @@ nsf_process_kernel(const NsfLaunch p) {
   typedef NsfGeo<ANA> G;
   extern __shared__ float4 nsf_smem4[];
   float* smem = reinterpret_cast<float*>(nsf_smem4);
-  float* s_win = smem;
-  float2* s_tw = reinterpret_cast<float2*>(smem + 256);
-  float* s_logi = smem + 768;
+  float* s_win = smem + kNsfImgWin;
+  float2* s_tw = reinterpret_cast<float2*>(smem + kNsfImgTw);
+  float* s_logi = smem + kNsfImgLogi;
+  float2* s_tw12 = reinterpret_cast<float2*>(smem + kNsfImgTw12);
+  mbar_t* bars = reinterpret_cast<mbar_t*>(smem + kNsfTableImgWords);
 
   const int lane = lane_id();
   const int warp = (int)(threadIdx.x >> 5);
   const NsfTables* T = p.tables;
-  for (int i = (int)threadIdx.x; i < ANA; i += kNsfWarpsPerCta * 32)
-    s_win[i] = ANA == 256 ? T->win256[i] : T->win128[i];
-  for (int i = (int)threadIdx.x; i < 256; i += kNsfWarpsPerCta * 32) s_tw[i] = T->tw[i];
-  for (int i = (int)threadIdx.x; i < 132; i += kNsfWarpsPerCta * 32) s_logi[i] = T->logi[i];
-  float2* s_tw12 = reinterpret_cast<float2*>(smem + 912);
-  __syncthreads();
-  fft_fill_tw12<G::kNC>(s_tw12, s_tw, (int)threadIdx.x, kNsfWarpsPerCta * 32);
-  __syncthreads();
-
   const int sidx = (int)blockIdx.x * kNsfWarpsPerCta + warp;
-  if (sidx >= p.n_streams) return;  // whole warp leaves; no block barriers below
+  const bool live = sidx < p.n_streams;
 
   float* W = smem + kNsfCtaTableWords + warp * NsfWarpWords<SPLIT, NB>::value;
   // Header scalars are double buffered: within a frame every lane reads the
@@ -244,62 +242,44 @@ nsf_process_kernel(const NsfLaunch p) {
   float2* blkP = reinterpret_cast<float2*>(X_magnP + kNsfAuxStride);  // split mode: Process block (dataBuf)
   float2* blkH = reinterpret_cast<float2*>(reinterpret_cast<float*>(ovl + 48) + (SPLIT ? 4 * kNsfAuxStride + 256 : 0));  // high-band delay blocks (dataBufHB)
 
-  const int slot = p.slots[sidx];
+  // ---- tables and state: HBM -> shared by TMA bulk copies.  Everything a stream needs is in
+  // flight after a handful of instructions of one lane and one dependent load (the slot), where
+  // the table loops, the header, the histories and the records used to be a chain of five
+  // dependent global-memory latencies per warp -- most of a launch that walks a single frame.
+  mbar_t* barT = bars;                 // tables (per CTA)
+  mbar_t* barH = bars + 1 + 2 * warp;  // header + sample histories: needed by the first window / FFT
+  mbar_t* barB = barH + 1;             // per-bin records (+ split arrays): awaited after the first FFT
+  if (threadIdx.x == 0) mbar_init(barT, 1);
+  if (lane == 0) {
+    mbar_init(barH, 1);
+    mbar_init(barB, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect(barT, sizeof(float) * kNsfTableImgWords);
+    bulk_load(smem, T->img[ANA == 256 ? 0 : 1], sizeof(float) * kNsfTableImgWords, barT);
+  }
+  const int slot = live ? (p.slots ? p.slots[sidx] : p.slot_base + sidx) : 0;
   float* gS = p.state + (size_t)slot * kNsfStateWords;
   int* gHist = p.hist + (size_t)slot * kNsfHistWords;
   float* gInitMagn = gS + kNsfOffInitMagn;
-
-  // ---- state: HBM -> shared / registers
-  Hr[lane] = gS[lane];
-  {
-    // per-bin records: asynchronous copy, awaited just before the first use (noise estimation)
-    const float4* src = reinterpret_cast<const float4*>(gS + kNsfOffBins);
-    float4* dst = reinterpret_cast<float4*>(B);
-    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) async_copy16(dst + i, src + i);
-    if (SPLIT) {
-      const float4* xs = reinterpret_cast<const float4*>(gS + kNsfOffAux);
-      float4* xd = reinterpret_cast<float4*>(X_noise);
-      for (int i = lane; i < 4 * kNsfAuxStride / 4; i += 32) async_copy16(xd + i, xs + i);
-    }
+  constexpr unsigned kHistBytes = G::kHP * sizeof(float2);             // 384 / 192
+  constexpr unsigned kBinBytes = G::kBins * kNsfBinRec * sizeof(float);  // 6192 / 3120
+  if (live && lane == 0) {
+    // sample histories: the tail of each block is what the previous frame left behind
+    mbar_arrive_expect(barH, kNsfHdrWords * 4 + (2 + (SPLIT ? 1 : 0) + (NB - 1)) * kHistBytes);
+    bulk_load(Hr, gS, kNsfHdrWords * 4, barH);
+    bulk_load(blkA + G::kFP, gS + kNsfOffXHist, kHistBytes, barH);
+    bulk_load(ovl, gS + kNsfOffSynt, kHistBytes, barH);
+    if (SPLIT) bulk_load(blkP + G::kFP, gS + kNsfOffPHist, kHistBytes, barH);
+#pragma unroll
+    for (int b = 0; b < NB - 1; ++b) bulk_load(blkH + 128 * b + G::kFP, gS + kNsfOffHb + 96 * b, kHistBytes, barH);
+    mbar_arrive_expect(barB, kBinBytes + (SPLIT ? 4 * kNsfAuxStride * 4 : 0));
+    bulk_load(B, gS + kNsfOffBins, kBinBytes, barB);
+    if (SPLIT) bulk_load(X_noise, gS + kNsfOffAux, 4 * kNsfAuxStride * 4, barB);
   }
   bool state_ready = false;
-  // sample histories: the tail of each block is what the previous frame left behind
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int pr = lane + 32 * u;
-    if (pr < G::kHP) {
-      blkA[G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffXHist)[pr];
-      ovl[pr] = reinterpret_cast<const float2*>(gS + kNsfOffSynt)[pr];
-      if (SPLIT) blkP[G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffPHist)[pr];
-#pragma unroll
-      for (int b = 0; b < NB - 1; ++b)
-        blkH[128 * b + G::kFP + pr] = reinterpret_cast<const float2*>(gS + kNsfOffHb + 96 * b)[pr];
-    }
-  }
-  __syncwarp();
-  if (SPLIT) {
-    async_copy_wait_all();
-    __syncwarp();
-    state_ready = true;
-    if (reinterpret_cast<const int*>(Hr)[kH_splitValid] == 0) {
-      // the stream was driven by the fused kernel so far: one frame for both sides means
-      // noise == noisePrev, magnPrevProcess == magnPrevAnalyze, dataBuf == analyzeBuf
-      for (int k = lane; k < G::kBins; k += 32) {
-        X_noise[k] = B[k * kNsfBinRec + kB_noisePrev];
-        X_magnP[k] = B[k * kNsfBinRec + kB_magnPrev];
-        X_prob[k] = 0.f;
-        X_param[k] = 0.f;
-      }
-      for (int pr = lane; pr < G::kHP; pr += 32) blkP[G::kFP + pr] = blkA[G::kFP + pr];
-      __syncwarp();
-    }
-  }
-
-  const float overdrive = Hr[kH_overdrive];
-  const float denoiseBound = Hr[kH_denoiseBound];
-  const int gainmap = reinterpret_cast<const int*>(Hr)[kH_gainmap];
-  constexpr float kMagnLenF = (float)G::kBins;
-  const float magnLenF = kMagnLenF;
 
   // PCM addressing: frame pair w of band b.
   const size_t in_base = (size_t)sidx * (size_t)p.in_stream_stride;
@@ -343,8 +323,35 @@ nsf_process_kernel(const NsfLaunch p) {
       if (w < G::kFP) pcm_load<I16>(dst[u], p.ana_in, off, w);
     }
   };
-  if (p.frames > 0) load_frame(0, cur);
-  if (SPLIT && p.frames > 0) load_ana(0, curA);
+  // the first frame's PCM goes out with the state copies, before anything is waited for
+  if (live && p.frames > 0) load_frame(0, cur);
+  if (SPLIT && live && p.frames > 0) load_ana(0, curA);
+
+  mbar_wait_cta(barT, 0);
+  if (!live) return;  // whole warp leaves; no block barriers below
+  mbar_wait_warp(barH, 0);
+  if (SPLIT) {
+    mbar_wait_warp(barB, 0);
+    state_ready = true;
+    if (reinterpret_cast<const int*>(Hr)[kH_splitValid] == 0) {
+      // the stream was driven by the fused kernel so far: one frame for both sides means
+      // noise == noisePrev, magnPrevProcess == magnPrevAnalyze, dataBuf == analyzeBuf
+      for (int k = lane; k < G::kBins; k += 32) {
+        X_noise[k] = B[k * kNsfBinRec + kB_noisePrev];
+        X_magnP[k] = B[k * kNsfBinRec + kB_magnPrev];
+        X_prob[k] = 0.f;
+        X_param[k] = 0.f;
+      }
+      for (int pr = lane; pr < G::kHP; pr += 32) blkP[G::kFP + pr] = blkA[G::kFP + pr];
+      __syncwarp();
+    }
+  }
+
+  const float overdrive = Hr[kH_overdrive];
+  const float denoiseBound = Hr[kH_denoiseBound];
+  const int gainmap = reinterpret_cast<const int*>(Hr)[kH_gainmap];
+  constexpr float kMagnLenF = (float)G::kBins;
+  const float magnLenF = kMagnLenF;
 
   // optional lock step of the CTA's warps (full CTAs only): warps in the same phase share
   // instruction-cache lines
@@ -462,8 +469,7 @@ nsf_process_kernel(const NsfLaunch p) {
       const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
 
       if (!state_ready) {
-        async_copy_wait_all();
-        __syncwarp();
+        mbar_wait_warp(barB, 0);
         state_ready = true;
       }
       // ---- (d) NoiseEstimation (ns_core.c:217-285)
@@ -1066,32 +1072,22 @@ nsf_process_kernel(const NsfLaunch p) {
     { float* t = Hr; Hr = Hw; Hw = t; }
   }
 
-  // ---- state: shared / registers -> HBM
-  if (!state_ready) async_copy_wait_all();
-  __syncwarp();
+  // ---- state: shared -> HBM, again as bulk copies issued by one lane
+  if (!state_ready) mbar_wait_warp(barB, 0);
   // the fused kernel does not maintain the split-mode arrays: mark them stale
-  gS[lane] = (lane == kH_splitValid && p.frames > 0) ? __int_as_float(SPLIT ? 1 : 0) : Hr[lane];
-  if (SPLIT) {
-    float4* xd = reinterpret_cast<float4*>(gS + kNsfOffAux);
-    const float4* xs = reinterpret_cast<const float4*>(X_noise);
-    for (int i = lane; i < 4 * kNsfAuxStride / 4; i += 32) xd[i] = xs[i];
-  }
-  {
-    float4* dst = reinterpret_cast<float4*>(gS + kNsfOffBins);
-    const float4* src = reinterpret_cast<const float4*>(B);
-    for (int i = lane; i < G::kBins * kNsfBinRec / 4; i += 32) dst[i] = src[i];
-  }
+  if (lane == kH_splitValid && p.frames > 0) reinterpret_cast<int*>(Hr)[kH_splitValid] = SPLIT ? 1 : 0;
+  bulk_store_fence();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(gS, Hr, kNsfHdrWords * 4);
+    bulk_store(gS + kNsfOffXHist, blkA + G::kFP, kHistBytes);
+    bulk_store(gS + kNsfOffSynt, ovl, kHistBytes);
+    if (SPLIT) bulk_store(gS + kNsfOffPHist, blkP + G::kFP, kHistBytes);
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int pr = lane + 32 * u;
-    if (pr < G::kHP) {
-      reinterpret_cast<float2*>(gS + kNsfOffXHist)[pr] = blkA[G::kFP + pr];
-      reinterpret_cast<float2*>(gS + kNsfOffSynt)[pr] = ovl[pr];
-      if (SPLIT) reinterpret_cast<float2*>(gS + kNsfOffPHist)[pr] = blkP[G::kFP + pr];
-#pragma unroll
-      for (int b = 0; b < NB - 1; ++b)
-        reinterpret_cast<float2*>(gS + kNsfOffHb + 96 * b)[pr] = blkH[128 * b + G::kFP + pr];
-    }
+    for (int b = 0; b < NB - 1; ++b) bulk_store(gS + kNsfOffHb + 96 * b, blkH + 128 * b + G::kFP, kHistBytes);
+    bulk_store(gS + kNsfOffBins, B, kBinBytes);
+    if (SPLIT) bulk_store(gS + kNsfOffAux, X_noise, 4 * kNsfAuxStride * 4);
+    bulk_store_drain();
   }
 }
 

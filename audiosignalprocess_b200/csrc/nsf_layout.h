@@ -54,8 +54,15 @@ enum : int {
   kB_noisePrev, kB_magnPrev, kB_logLrt, kB_magnAvgPause
 };
 
-// Read-only per-device tables.
+// Read-only per-device tables.  img[v] (v = 0: 256-point analysis, 1: 128-point) is the image of
+// the kernel's per-CTA table block exactly as it sits in shared memory -- window | twiddles |
+// log(i) | pad | twiddles of FFT passes 1-2 regrouped per (factor, lane) (ns_warp.cuh
+// fft_fill_tw12) -- so that a CTA fetches it with one TMA bulk copy.
+enum : int {
+  kNsfImgWin = 0, kNsfImgTw = 256, kNsfImgLogi = 768, kNsfImgTw12 = 912, kNsfTableImgWords = 1152,
+};
 struct NsfTables {
+  alignas(16) float img[2][kNsfTableImgWords];
   float win256[256];  // kBlocks160w256  windows_private.h:94
   float win128[128];  // kBlocks80w128   windows_private.h:64
   float2 tw[256];     // e^{+2 pi i t/256}
@@ -67,7 +74,8 @@ struct NsfTables {
 struct NsfLaunch {
   float* state;            // slab base
   int* hist;               // cold histogram slab base
-  const int* slots;        // [n_streams] slab index per batch entry
+  const int* slots;        // [n_streams] slab index per batch entry; NULL: entry i sits in slot slot_base + i
+  int slot_base = 0;
   const NsfTables* tables;
   const void* in;          // int16 or float samples
   void* out;
