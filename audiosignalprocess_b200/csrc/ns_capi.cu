@@ -593,7 +593,8 @@ int LaunchNs(DeviceCtx& d, uint32_t magic, int ana, int nb, int n, const int16_t
   }
   NsxLaunch p;
   p.state = (uint32_t*)d.x_state.base;
-  p.slots = d.d_slots;
+  p.slots = d.slot_run >= n ? nullptr : d.d_slots;
+  p.slot_base = d.slot_run >= n ? d.cached_slots[0] : 0;
   p.tables = d.d_nsx_tables;
   p.in = in + (size_t)f0 * fstride;
   p.out = out + (size_t)f0 * fstride;

@@ -578,7 +578,13 @@ nsf_process_kernel(const NsfLaunch p) {
           if (pinkExp == 0.f) {
             parametric[j] = white;
           } else {
-            const float ub = (float)(k < 5 ? 5 : k);
+            // opaque to the optimiser: the bin index is loop-invariant, and with it powf's
+            // log2(ub) was hoisted out of the frame loop into the kernel prologue -- 200
+            // instructions per launch for a branch taken during a stream's first half second
+            // (8 % of a launch that walks one frame)
+            int kub = k < 5 ? 5 : k;
+            asm volatile("" : "+r"(kub));
+            const float ub = (float)kub;
             parametric[j] = pnum / powf(ub, pexp);
           }
           noise[j] *= (float)blockInd;

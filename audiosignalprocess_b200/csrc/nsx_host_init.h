@@ -88,6 +88,14 @@ inline void nsx_fill_tables(NsxTables* t) {
   };
   sums(5, &t->sum_log_idx5, &t->sum_sq_log_idx5, &t->det5);
   sums(65, &t->sum_log_idx65, &t->sum_sq_log_idx65, nullptr);
+  // shared-memory images (nsx_layout.h)
+  for (int v = 0; v < 2; ++v) {
+    uint32_t* img = t->img[v];
+    memset(img, 0, sizeof(t->img[v]));
+    memcpy(img, v == 0 ? (const void*)t->win256 : (const void*)t->win128, v == 0 ? sizeof(t->win256) : sizeof(t->win128));
+    memcpy(img + 128, t->tw, sizeof(t->tw));
+    memcpy(img + 256, t->log_frac, sizeof(t->log_frac));
+  }
 }
 
 inline void nsx_set_mode(uint32_t* slab, int mode) {

@@ -38,7 +38,10 @@ constexpr int kNsxMaxWarpsPerCta = 28;    // 72 registers x 896 threads, 168 KB 
 #ifndef NSX_FRAME_SYNC
 #define NSX_FRAME_SYNC 1
 #endif
-constexpr int kNsxCtaTableWords = 128 + 128 + 128;   // window | twiddles | log2 fraction table
+// per CTA: table image (window | twiddles | log2 fraction table) | mbarriers of the TMA bulk copies
+// (one for the tables, two per warp: header + sample histories | per-bin records)
+constexpr int kNsxCtaBarWords = (2 * (1 + 2 * kNsxMaxWarpsPerCta) + 3) / 4 * 4;
+constexpr int kNsxCtaTableWords = kNsxTableImgWords + kNsxCtaBarWords;
 constexpr int kNsxScratchWords = 256 + 136;          // FFT transposes | time / spectrum buffer
 constexpr int kNsxWarpWords = 2 * kNsxHdrWords + 2 * 129 * 4 + kNsxScratchWords;
 
@@ -207,14 +210,8 @@ nsx_process_kernel(const NsxLaunch p) {
   const int warp = (int)(threadIdx.x >> 5);
   const NsxTables* T = p.tables;
   const int warps_per_cta = (int)(blockDim.x >> 5);
-  for (int i = (int)threadIdx.x; i < ANA; i += (int)blockDim.x)
-    s_win[i] = ANA == 256 ? T->win256[i] : T->win128[i];
-  for (int i = (int)threadIdx.x; i < 128; i += (int)blockDim.x) s_tw[i] = T->tw[i];
-  for (int i = (int)threadIdx.x; i < 256; i += (int)blockDim.x) s_logf[i] = T->log_frac[i];
-  __syncthreads();
-
   const int sidx = (int)blockIdx.x * warps_per_cta + warp;
-  if (sidx >= p.n_streams) return;
+  const bool live = sidx < p.n_streams;
 
   uint32_t* W = smem + kNsxCtaTableWords + warp * kNsxWarpWords;
   int* Hr = reinterpret_cast<int*>(W);                   // header, double buffered (see nsf_kernel.cuh)
@@ -224,40 +221,42 @@ nsx_process_kernel(const NsxLaunch p) {
   uint32_t* scr = reinterpret_cast<uint32_t*>(RB + 129);  // 256 words: FFT transposes
   uint32_t* buf = scr + 256;                              // 136 words: time / spectrum staging
 
-  const int slot = p.slots[sidx];
+  // ---- tables and state: HBM -> shared by TMA bulk copies issued by one lane (see nsf_kernel.cuh);
+  // the sample histories pass through the FFT scratch on their way to registers
+  mbar_t* bars = reinterpret_cast<mbar_t*>(smem + kNsxTableImgWords);
+  mbar_t* barT = bars;
+  mbar_t* barH = bars + 1 + 2 * warp;   // header + sample histories
+  mbar_t* barB = barH + 1;              // per-bin records: awaited before the noise estimation
+  if (threadIdx.x == 0) mbar_init(barT, 1);
+  if (lane == 0) {
+    mbar_init(barH, 1);
+    mbar_init(barB, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect(barT, sizeof(uint32_t) * kNsxTableImgWords);
+    bulk_load(smem, T->img[ANA == 256 ? 0 : 1], sizeof(uint32_t) * kNsxTableImgWords, barT);
+  }
+  const int slot = live ? (p.slots ? p.slots[sidx] : p.slot_base + sidx) : 0;
   uint32_t* gS = p.state + (size_t)slot * kNsxStateWords;
   int* gHist = reinterpret_cast<int*>(gS + kNsxOffHist);
   uint32_t* gInit = gS + kNsxOffInitMagn;
   const bool act = lane < LANES;
-
-  // ---- state: HBM -> shared / registers
-  Hr[lane] = (int)gS[lane];
-  // per-bin records: asynchronous copy (cp.async), awaited before the first use
-  for (int i = lane; i < NBIN; i += 32) {
-    async_copy16(&RA[i], reinterpret_cast<const uint4*>(gS + kNsxOffRecA) + i);
-    async_copy16(&RB[i], reinterpret_cast<const uint4*>(gS + kNsxOffRecB) + i);
+  constexpr unsigned kHistBytes = LANES * 3 * sizeof(int16_t);   // 192 / 96
+  constexpr unsigned kRecBytes = NBIN * sizeof(uint4);           // 2064 / 1040
+  if (live && lane == 0) {
+    mbar_arrive_expect(barH, kNsxHdrWords * 4 + (2 + (NB - 1)) * kHistBytes);
+    bulk_load(Hr, gS, kNsxHdrWords * 4, barH);
+    bulk_load(scr, gS + kNsxOffAna, kHistBytes, barH);
+    bulk_load(scr + 48, gS + kNsxOffSyn, kHistBytes, barH);
+#pragma unroll
+    for (int b = 0; b < NB - 1; ++b) bulk_load(scr + 96 + 48 * b, gS + kNsxOffHb + 48 * b, kHistBytes, barH);
+    mbar_arrive_expect(barB, 2 * kRecBytes);
+    bulk_load(RA, gS + kNsxOffRecA, kRecBytes, barB);
+    bulk_load(RB, gS + kNsxOffRecB, kRecBytes, barB);
   }
   bool state_ready = false;
-  int ana_h[3], syn_h[3], hb_h[NB > 1 ? NB - 1 : 1][3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    ana_h[r] = syn_h[r] = 0;
-    if (act) {
-      ana_h[r] = reinterpret_cast<const int16_t*>(gS + kNsxOffAna)[lane + LANES * r];
-      syn_h[r] = reinterpret_cast<const int16_t*>(gS + kNsxOffSyn)[lane + LANES * r];
-    }
-#pragma unroll
-    for (int b = 0; b < NB - 1; ++b)
-      hb_h[b][r] = act ? reinterpret_cast<const int16_t*>(gS + kNsxOffHb + 48 * b)[lane + LANES * r] : 0;
-  }
-  __syncwarp();
-
-  const int overdrive = Hr[kX_overdrive];
-  const int denoise_bound = Hr[kX_denoiseBound];
-  const int gain_map = Hr[kX_gainMap];
-  const int mode = Hr[kX_mode];
-  const int max_lrt = ANA == 256 ? 0x0080000 : 0x0040000;
-  const int min_lrt = ANA == 256 ? 104858 : 52429;
 
   const int16_t* gin = static_cast<const int16_t*>(p.in) + (size_t)sidx * (size_t)p.in_stream_stride;
   int16_t* gout = static_cast<int16_t*>(p.out) + (size_t)sidx * (size_t)p.out_stream_stride;
@@ -272,7 +271,32 @@ nsx_process_kernel(const NsxLaunch p) {
       for (int r = 0; r < 5; ++r) dst[b][r] = act ? (int)src[lane + LANES * r] : 0;
     }
   };
-  if (p.frames > 0) load_frame(0, cur);
+  // the first frame's PCM goes out with the state copies, before anything is waited for
+  if (live && p.frames > 0) load_frame(0, cur);
+
+  mbar_wait_cta(barT, 0);
+  if (!live) return;
+  mbar_wait_warp(barH, 0);
+  int ana_h[3], syn_h[3], hb_h[NB > 1 ? NB - 1 : 1][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    ana_h[r] = syn_h[r] = 0;
+    if (act) {
+      ana_h[r] = reinterpret_cast<const int16_t*>(scr)[lane + LANES * r];
+      syn_h[r] = reinterpret_cast<const int16_t*>(scr + 48)[lane + LANES * r];
+    }
+#pragma unroll
+    for (int b = 0; b < NB - 1; ++b)
+      hb_h[b][r] = act ? reinterpret_cast<const int16_t*>(scr + 96 + 48 * b)[lane + LANES * r] : 0;
+  }
+  __syncwarp();
+
+  const int overdrive = Hr[kX_overdrive];
+  const int denoise_bound = Hr[kX_denoiseBound];
+  const int gain_map = Hr[kX_gainMap];
+  const int mode = Hr[kX_mode];
+  const int max_lrt = ANA == 256 ? 0x0080000 : 0x0040000;
+  const int min_lrt = ANA == 256 ? 104858 : 52429;
 
   // optional lock step of the CTA's warps (full CTAs only): warps in the same phase share
   // instruction-cache lines
@@ -501,8 +525,7 @@ nsx_process_kernel(const NsxLaunch p) {
       }
 
       if (!state_ready) {
-        async_copy_wait_all();
-        __syncwarp();
+        mbar_wait_warp(barB, 0);
         state_ready = true;
       }
       NSX_PHASE_SYNC();
@@ -1213,23 +1236,29 @@ nsx_process_kernel(const NsxLaunch p) {
     { int* t = Hr; Hr = Hw; Hw = t; }
   }
 
-  // ---- state: shared / registers -> HBM
-  if (!state_ready) async_copy_wait_all();
-  __syncwarp();
-  gS[lane] = (uint32_t)Hr[lane];
-  for (int i = lane; i < NBIN; i += 32) {
-    reinterpret_cast<uint4*>(gS + kNsxOffRecA)[i] = RA[i];
-    reinterpret_cast<uint4*>(gS + kNsxOffRecB)[i] = RB[i];
-  }
+  // ---- state: shared / registers -> HBM (bulk copies; the histories go back through the scratch)
+  if (!state_ready) mbar_wait_warp(barB, 0);
   if (act) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      reinterpret_cast<int16_t*>(gS + kNsxOffAna)[lane + LANES * r] = (int16_t)ana_h[r];
-      reinterpret_cast<int16_t*>(gS + kNsxOffSyn)[lane + LANES * r] = (int16_t)syn_h[r];
+      reinterpret_cast<int16_t*>(scr)[lane + LANES * r] = (int16_t)ana_h[r];
+      reinterpret_cast<int16_t*>(scr + 48)[lane + LANES * r] = (int16_t)syn_h[r];
 #pragma unroll
       for (int b = 0; b < NB - 1; ++b)
-        reinterpret_cast<int16_t*>(gS + kNsxOffHb + 48 * b)[lane + LANES * r] = (int16_t)hb_h[b][r];
+        reinterpret_cast<int16_t*>(scr + 96 + 48 * b)[lane + LANES * r] = (int16_t)hb_h[b][r];
     }
+  }
+  bulk_store_fence();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(gS, Hr, kNsxHdrWords * 4);
+    bulk_store(gS + kNsxOffAna, scr, kHistBytes);
+    bulk_store(gS + kNsxOffSyn, scr + 48, kHistBytes);
+#pragma unroll
+    for (int b = 0; b < NB - 1; ++b) bulk_store(gS + kNsxOffHb + 48 * b, scr + 96 + 48 * b, kHistBytes);
+    bulk_store(gS + kNsxOffRecA, RA, kRecBytes);
+    bulk_store(gS + kNsxOffRecB, RB, kRecBytes);
+    bulk_store_drain();
   }
 }
 

@@ -53,7 +53,11 @@ enum : int {
 
 // Read-only tables (built by formula in nsx_host_init.h; the literal reference
 // tables they reproduce are cited there).
+// img[v] (v = 0: 256-point analysis, 1: 128-point) is the image of the kernel's per-CTA table block as
+// it sits in shared memory (window | twiddles | log2 fraction table), fetched with one TMA bulk copy.
+enum : int { kNsxTableImgWords = 128 + 128 + 128 };
 struct NsxTables {
+  alignas(16) uint32_t img[2][kNsxTableImgWords];
   int16_t win256[256];
   int16_t win128[128];
   uint32_t tw[128];         // (cos, sin)(2 pi t / 256) packed int16 pairs from kSinTable1024
@@ -70,7 +74,8 @@ struct NsxTables {
 
 struct NsxLaunch {
   uint32_t* state;
-  const int* slots;
+  const int* slots;        // [n_streams] slab index per batch entry; NULL: entry i sits in slot slot_base + i
+  int slot_base = 0;
   const NsxTables* tables;
   const void* in;   // int16 samples
   void* out;
