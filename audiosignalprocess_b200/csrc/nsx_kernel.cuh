@@ -226,7 +226,7 @@ nsx_process_kernel(const NsxLaunch p) {
   mbar_t* bars = reinterpret_cast<mbar_t*>(smem + kNsxTableImgWords);
   mbar_t* barT = bars;
   mbar_t* barH = bars + 1 + 2 * warp;   // header + sample histories
-  mbar_t* barB = barH + 1;              // per-bin records: awaited before the noise estimation
+  mbar_t* barB = barH + 1;              // per-bin records
   if (threadIdx.x == 0) mbar_init(barT, 1);
   if (lane == 0) {
     mbar_init(barH, 1);
@@ -256,7 +256,6 @@ nsx_process_kernel(const NsxLaunch p) {
     bulk_load(RA, gS + kNsxOffRecA, kRecBytes, barB);
     bulk_load(RB, gS + kNsxOffRecB, kRecBytes, barB);
   }
-  bool state_ready = false;
 
   const int16_t* gin = static_cast<const int16_t*>(p.in) + (size_t)sidx * (size_t)p.in_stream_stride;
   int16_t* gout = static_cast<int16_t*>(p.out) + (size_t)sidx * (size_t)p.out_stream_stride;
@@ -277,6 +276,10 @@ nsx_process_kernel(const NsxLaunch p) {
   mbar_wait_cta(barT, 0);
   if (!live) return;
   mbar_wait_warp(barH, 0);
+  // (waiting for the records here rather than before their first use costs nothing measurable --
+  // both copies are in flight together -- and keeps a pointer and a flag out of the frame loop's
+  // 72 registers)
+  mbar_wait_warp(barB, 0);
   int ana_h[3], syn_h[3], hb_h[NB > 1 ? NB - 1 : 1][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -524,10 +527,6 @@ nsx_process_kernel(const NsxLaunch p) {
         Hw[kX_featFlat] = (int)feat_flat;
       }
 
-      if (!state_ready) {
-        mbar_wait_warp(barB, 0);
-        state_ready = true;
-      }
       NSX_PHASE_SYNC();
       // ---- NoiseEstimation (nsx_core.c:334-452)
       unsigned noise[NSLOT];
@@ -1237,7 +1236,6 @@ nsx_process_kernel(const NsxLaunch p) {
   }
 
   // ---- state: shared / registers -> HBM (bulk copies; the histories go back through the scratch)
-  if (!state_ready) mbar_wait_warp(barB, 0);
   if (act) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {

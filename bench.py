@@ -9,7 +9,10 @@ call walking F = --frames-per-step 10-ms frames of every stream; with the defaul
   value     PCM resident in HBM, WebRtcNs_ProcessBatchDevice, CUDA events on the launch stream
   e2e       same steps through WebRtcNs_ProcessBatch with pinned HOST buffers
             (H2D + kernels + D2H inside the timed region)
-  roofline  HBM: algorithmic bytes B(F) = IO + 2*S_hot/F per stream-frame
+  roofline  HBM: algorithmic bytes B(F) = IO + 2*S_hot/F per stream-frame; at F = 100 the
+            kernel is issue-bound (roofline.issue), so the HBM fraction is small by construction
+  roofline_tick  the same kernel at F = 1 over --tick-streams streams (the API-faithful 10 ms tick, every
+            launch moves the whole per-stream state): the regime the HBM roofline bounds
   cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref) on the host cores
 
 N > 1: one process per GPU under torchrun, every rank owns its own 4096 streams (weak scaling,
@@ -40,13 +43,14 @@ def measured_traffic(kernel, frames_per_launch, streams):
     """DRAM bytes per launch of the dominant kernel from the committed ncu summary of the SAME
     configuration (profiles/r1_*.json), else None."""
     tag = {"nsf_process_kernel": "nsf", "nsx_process_kernel": "nsx"}.get(kernel)
-    path = os.path.join(ROOT, "profiles", "r1_%s_kernel_F%d.json" % (tag, frames_per_launch))
-    try:
-        d = json.load(open(path))
-        if d["units_per_launch"] == streams * frames_per_launch:
-            return d["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    for name in ("r1_%s_kernel_F%d.json" % (tag, frames_per_launch),
+                 "r1_%s_kernel_F%d_%d.json" % (tag, frames_per_launch, streams)):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if d["units_per_launch"] == streams * frames_per_launch:
+                return d["dram_bytes_per_launch"]
+        except Exception:
+            pass
     return None
 
 
@@ -161,6 +165,53 @@ def cpu_reference_run(kind, fs, mode, streams, frames, threads):
     return streams * frames * 0.01 / sec
 
 
+def tick_roofline(a, pkg, lib, torch, dev, stream, kind):
+    """The API-faithful 10 ms tick (the regime the HBM roofline is meaningful for): ONE frame per
+    stream per call over --tick-streams streams, so that every launch loads and stores the whole per-stream
+    state (B(1) = IO + 2*S_hot bytes per stream-frame) and the state of all streams (360 MB float / 16 kHz at
+    32768 streams) cannot stay in the 126 MB L2.  Timed in steady state, past the 50 start-up frames."""
+    n, fl = a.tick_streams, a.fs // 100
+    warm, steps = 60, 200
+    total = (warm + steps) * fl
+    pcm_in = torch.empty((n, total), dtype=torch.int16, device=dev)
+    pcm_out = torch.empty_like(pcm_in)
+    rc = lib.WebRtcNsB200_SynthPcmDevice(C.c_void_p(pcm_in.data_ptr()), total, n, 0, a.fs, 0, total, 4321,
+                                         C.c_void_p(stream.cuda_stream))
+    assert rc == 0, lib.WebRtcNsB200_LastError()
+    batch = pkg.NsBatch(n, a.fs, a.mode, fixed=a.fixed, devices=[dev.index])
+
+    def tick(i):
+        off = i * fl * 2
+        batch.process_device(pcm_in.data_ptr() + off, total, pcm_out.data_ptr() + off, total, 1, stream.cuda_stream)
+
+    for i in range(warm):
+        tick(i)
+    torch.cuda.synchronize()
+    # one event pair per launch: the kernel's own duration, without the host's gap between two calls
+    # (at ~130 us per tick the Python caller does not always keep the GPU fed; `tick_ms_wall` shows it)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record(stream)
+        tick(warm + i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    per = sorted(x.elapsed_time(y) for x, y in ev)
+    avg_ms = sum(per) / steps
+    wall_ms = ev[0][0].elapsed_time(ev[-1][1]) / steps
+    batch.close()
+    peak, which = measured_peak_gbs()
+    bsf = algorithmic_bytes(kind, a.fs, 1)
+    achieved = bsf * n / (avg_ms * 1e-3) / 1e9
+    kname = "nsx_process_kernel" if a.fixed else "nsf_process_kernel"
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": measured_traffic(kname, 1, n) if a.fs == 16000 else None, "peak_source": which, "kernel": kname,
+            "workload": "%d streams x 1 frame per launch (10 ms tick), %d launches after %d warm-up ticks; "
+                        "state %.0f MB > L2" % (n, steps, warm, n * S_HOT[(kind, a.fs)] / 1e6),
+            "bytes_per_stream_frame": bsf, "frames_per_launch": 1, "launch_ms_avg": avg_ms,
+            "launch_ms_median": per[len(per) // 2], "tick_ms_wall": wall_ms,
+            "value": n * 0.01 / (avg_ms * 1e-3), "value_unit": "audio-s/s"}
+
+
 def config5(a, pkg, lib, torch, dist, rank, local_rank, world, barrier):
     """BASELINE configs[4] / SURVEY.md 8d(5): --total-streams streams x --seconds at 16 kHz, each rank owning a
     contiguous slice; PCM generated on the device per chunk of F frames, output reduced on the device to a
@@ -253,6 +304,9 @@ def main():
                          "by chunk, sharded over the ranks, output reduced to per-stream checksums (strong scaling)")
     ap.add_argument("--total-streams", type=int, default=65536)
     ap.add_argument("--seconds", type=int, default=600)
+    ap.add_argument("--tick-streams", type=int, default=32768,
+                    help="streams of the one-frame-per-launch leg (roofline_tick; rank 0 at N=1 only)")
+    ap.add_argument("--no-tick", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -445,11 +499,16 @@ def main():
                 cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",
                        "sample": "%d streams x %d frames (%.0f s of audio each), %d pthreads, one stream per core at a time"
                                  % (streams, frames, frames * 0.01, cores)}
+        tick = None
+        if world == 1 and not a.no_tick and F != 1:
+            del pcm_in, pcm_out
+            torch.cuda.empty_cache()
+            tick = tick_roofline(a, pkg, lib, torch, dev, stream, kind)
         line = {"metric": "ns_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32" if a.fixed else "f32",
                 "data": "synthetic", "config": config, "clocks": sampler.summary(), "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_tick": tick, "cpu_baseline": cpu}
         print(json.dumps(line))
     batch.close()
     if world > 1:
