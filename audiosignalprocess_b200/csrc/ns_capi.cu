@@ -134,9 +134,14 @@ void DrainPendingLocked() {
   for (PendingBatch& p : g_pending) FinishPending(p);
   g_pending.clear();
 }
+// true between CheckBatch and the end of the API call: the call's handle list IS g_memo.hs, so the
+// helpers below need not compare 8 bytes per stream again (a one-frame tick over 32768 streams is
+// ~125 us of GPU time; the host side of the call has to stay well below that)
+bool g_call_is_memo = false;
 struct ApiLock {
   std::lock_guard<std::mutex> guard;
   explicit ApiLock(bool drain = true) : guard(g_mu) {
+    g_call_is_memo = false;
     if (drain && !g_pending.empty()) DrainPendingLocked();
   }
 };
@@ -246,6 +251,7 @@ struct BatchMemo {
   std::vector<Handle*> hs;      // ... validated
   std::vector<int> slots;       // RunDevice's slot list for exactly `hs` (empty = not built)
   bool any_split = false;       // some handle of `hs` is in two-signal mode
+  int single_dev = -1;          // the device all of `hs` live on, -1 if they span several
 };
 BatchMemo g_memo;
 
@@ -503,6 +509,7 @@ int LaunchNsf(int ana, int nb, bool i16, bool split, const NsfLaunch& p, cudaStr
 // histories and magnitude memories differ, so later fused calls on it run the split kernel with
 // the Process signal fed to both (identical results to the reference either way).
 bool SameAsMemo(const std::vector<Handle*>& hs) {
+  if (g_call_is_memo && g_memo.epoch == g_epoch && g_memo.hs.size() == hs.size()) return true;
   return g_memo.epoch == g_epoch && g_memo.hs.size() == hs.size() &&
          memcmp(g_memo.hs.data(), hs.data(), sizeof(Handle*) * hs.size()) == 0;
 }
@@ -853,12 +860,14 @@ int CheckBatch(void* const* hv, int n, uint32_t magic, size_t in_stride, size_t 
   } else {
     hs->resize(n);
     bool any_split = false;
+    int single_dev = -1;
     for (int i = 0; i < n; ++i) {
       Handle* h = AsHandle(hv[i], magic);
       if (!h) return Fail("bad handle in batch");
       if (!h->init_flag) return Fail("handle not initialised");
       if (h->fs != static_cast<Handle*>(hv[0])->fs) return Fail("mixed sample rates in one batch");
       any_split = any_split || h->split_mode;
+      single_dev = i == 0 ? h->dev : (single_dev == h->dev ? single_dev : -1);
       (*hs)[i] = h;
     }
     g_memo.epoch = g_epoch;
@@ -867,20 +876,21 @@ int CheckBatch(void* const* hv, int n, uint32_t magic, size_t in_stride, size_t 
     g_memo.hs = *hs;
     g_memo.slots.clear();
     g_memo.any_split = any_split;
+    g_memo.single_dev = single_dev;
   }
   const size_t need = (size_t)frames * ((*hs)[0]->fs / 100);
   if (n > 1 && (in_stride < need || out_stride < need)) return Fail("stride shorter than the frames of one stream");
+  g_call_is_memo = true;
   return 0;
 }
 
 int BatchDevice(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
                 int16_t* out, size_t out_stride, int frames, void* stream) {
   ApiLock lk;
-  std::vector<Handle*> hs;
+  static std::vector<Handle*> hs;   // (under the API lock) keeps its capacity: no 256 KB allocation per tick
   if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
   if (frames == 0) return 0;
-  for (int i = 1; i < n; ++i)
-    if (hs[i]->dev != hs[0]->dev) return Fail("device batch spans several GPUs");
+  if (g_memo.single_dev < 0) return Fail("device batch spans several GPUs");
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
