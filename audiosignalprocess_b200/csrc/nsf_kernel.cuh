@@ -404,7 +404,12 @@ nsf_process_kernel(const NsfLaunch p) {
         energy1 += v[j].x * v[j].x + v[j].y * v[j].y;
       }
     }
-    energy1 = warp_sum(energy1);
+    // Energy (ns_core.c:951) is a sum of squares: zero iff every term is, so the zero-input test is
+    // one vote, and the five dependent shuffle + add steps of the sum itself (needed only by the
+    // gain compensation much later) are issued next to the FFT, where there is independent work to
+    // hide them behind.  The reductions are a tenth of this kernel's stall samples.
+    const bool nzA = __any_sync(kFullMask, energy1 != 0.f);
+    bool nzP = nzA;   // the same frame on the Process side unless SPLIT
 
     float2 o0[kU];  // band-0 output pairs
     float hbGain = 1.f;
@@ -417,15 +422,15 @@ nsf_process_kernel(const NsfLaunch p) {
     float noise[G::kSlots], prevEst[G::kSlots], parametric[G::kSlots], prob[G::kSlots];
     float noisePrev[G::kSlots], logLrt[G::kSlots], mpause[G::kSlots];
     float prior = 0.f;
-    const float energyA = energy1;   // energy of the analysed frame (ns_core.c:1071)
 
-    if (energyA != 0.f) {
+    if (nzA) {   // energy of the analysed frame != 0 (ns_core.c:1071)
       // ======== WebRtcNs_AnalyzeCore (zero input: no statistics update, ns_core.c:1072-1082)
       blockInd = HIr[kH_blockInd] + 1;
       HIw[kH_blockInd] = blockInd;
       const int updateParsFlag = HIr[kH_modelUpd0];
 
       // ---- (c) forward FFT (ns_core.c:886-911)
+      if (!SPLIT) energy1 = warp_sum(energy1);
       warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
       if (lane < G::kL) {
 #pragma unroll
@@ -465,13 +470,14 @@ nsf_process_kernel(const NsfLaunch p) {
           }
         }
       }
-      warp_sum2(sigE, sumMagn);
-      const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
-
       if (!state_ready) {
         mbar_wait_warp(barB, 0);
         state_ready = true;
       }
+      // (after the wait: in one basic block with the tracker updates below, which hide its latency)
+      warp_sum2(sigE, sumMagn);
+      const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
+
       // ---- (d) NoiseEstimation (ns_core.c:217-285)
       int updates = HIr[kH_updates];
       if (updates < 200) updates++;
@@ -625,7 +631,19 @@ nsf_process_kernel(const NsfLaunch p) {
           if (k >= 1) sumLog += lmagn[j];
         }
       }
-      warp_sum2(sumPause, sumLog);
+      // first loop of (i) SpeechNoiseProb (ns_core.c:660-679) here: it needs nothing from (h), and its
+      // sum shares one reduction with the two above instead of paying a reduction latency of its own
+      float lsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < G::kSlots; ++j) {
+        const bool nyq = (j == G::kSlots - 1);
+        const float t1 = 1.f + 2.f * snrPrior[j];
+        const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
+        const float bessel = (snrPost[j] + 1.f) * t2;
+        logLrt[j] += 0.5f * (bessel - nsb_logf(t1) - logLrt[j]);
+        if (!nyq || lane == 0) lsum += logLrt[j];
+      }
+      warp_sum3(sumPause, sumLog, lsum);
 
       // ---- (h) FeatureUpdate (ns_core.c:755-791)
       float feat0, feat4;
@@ -695,17 +713,6 @@ nsf_process_kernel(const NsfLaunch p) {
 
       // ---- (i) SpeechNoiseProb (ns_core.c:642-749)
       {
-        float lsum = 0.f;
-#pragma unroll
-        for (int j = 0; j < G::kSlots; ++j) {
-          const bool nyq = (j == G::kSlots - 1);
-          const float t1 = 1.f + 2.f * snrPrior[j];
-          const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
-          const float bessel = (snrPost[j] + 1.f) * t2;
-          logLrt[j] += 0.5f * (bessel - nsb_logf(t1) - logLrt[j]);
-          if (!nyq || lane == 0) lsum += logLrt[j];
-        }
-        lsum = warp_sum(lsum);
         const float lrtAvg = NSB_FDIV_C(lsum, kMagnLenF);
         Hw[kH_feat + 3] = lrtAvg;
         // priorModelPars may have been re-estimated a few lines up (synced): read Hw
@@ -813,7 +820,8 @@ nsf_process_kernel(const NsfLaunch p) {
         }
       }
       energy1 = warp_sum(energy1);
-      if (energy1 != 0.f) {
+      nzP = energy1 != 0.f;
+      if (nzP) {
         warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
         if (lane < G::kL) {
 #pragma unroll
@@ -851,7 +859,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
     }
 
-    if (energy1 == 0.f) {
+    if (!nzP) {
       // ---- zero input to Process (ns_core.c:1239-1264): flush the overlap, high bands pass
       // through the delay line ungained.
 #pragma unroll

@@ -96,6 +96,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) r |= (simt_emu::shfl(pred ? 1u : 0u, l) & 1u) << l;
   return r;
 }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&simt_emu::ctx.warp->bar); }
 inline void __syncthreads() { pthread_barrier_wait(&simt_emu::ctx.block->bar); }
 inline void __threadfence_block() { __sync_synchronize(); }
