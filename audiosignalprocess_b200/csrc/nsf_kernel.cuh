@@ -18,9 +18,10 @@
 //        slab: header scalars | analysis history | synthesis overlap | HB
 //        delay lines | initMagnEst | per-bin records of 12 floats), plus a
 //        cold slab of 3x1000 histogram counters per stream.
-//   SMEM per warp: header, per-bin records, FFT scratch. Per CTA: window,
-//        twiddles, log(i) table.
-//   REGS analysis history / synthesis overlap (pairs of samples per lane).
+//   SMEM per warp: header (double buffered), per-bin records, FFT scratch, analysis block
+//        [history | frame], synthesis overlap. Per CTA: window, twiddles, log(i) table,
+//        mbarriers.  State and tables arrive and leave as TMA bulk copies issued by one lane.
+//   REGS the frame in flight: spectrum slots, per-bin statistics, prefetched PCM words.
 #ifndef AUDIOSIGNALPROCESS_B200_NSF_KERNEL_CUH_
 #define AUDIOSIGNALPROCESS_B200_NSF_KERNEL_CUH_
 
@@ -29,8 +30,8 @@
 
 namespace nsb200 {
 
-// 2-warp CTAs, 7 per SM (<= 146 registers): 14 resident streams per SM, so that the
-// headline 4096-stream batch is exactly two balanced rounds over 148 SMs.
+// 2-warp CTAs, 8 per SM (128 registers, no spills): 16 resident streams per SM -- the best of
+// 7/8/9/10 CTAs per SM and of 1/2/4/8 warps per CTA on the B200 (profiles/README.md).
 #ifndef NSF_WARPS_PER_CTA
 #define NSF_WARPS_PER_CTA 2
 #endif

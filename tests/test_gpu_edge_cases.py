@@ -169,3 +169,33 @@ def test_changing_handle_lists_between_calls(nslib, reflib):
     assert lib.WebRtcNsx_ProcessBatch(full, 8, x16.ctypes.data_as(C.c_void_p), x16.shape[1],
                                       out.ctypes.data_as(C.c_void_p), out.shape[1], 1) == -1
     b.close()
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_computed_and_listed_slots_agree(nslib, fixed):
+    """Handles created one after the other sit in consecutive state slots, and the kernels then compute
+    a stream's slot instead of loading it from the slot list; a permuted handle list takes the list
+    path.  Both must produce the same bits, tick by tick (state round-trips HBM through the TMA
+    bulk copies every call)."""
+    n, fs, mode, frames = 37, 16000, 2, 12
+    lib = nslib.load_library()
+    x = nslib.synth_pcm_host(n, fs, frames * 160)
+    a = nslib.NsBatch(n, fs, mode, fixed=fixed)
+    ref = np.zeros_like(x)
+    for f in range(frames):      # one frame per call
+        ref[:, f * 160:(f + 1) * 160] = a.process(np.ascontiguousarray(x[:, f * 160:(f + 1) * 160]))
+    a.close()
+    b = nslib.NsBatch(n, fs, mode, fixed=fixed)
+    perm = list(reversed(range(n)))
+    hv = (C.c_void_p * n)(*[b._handles[p] for p in perm])
+    fn = lib.WebRtcNsx_ProcessBatch if fixed else lib.WebRtcNs_ProcessBatch
+    out = np.zeros_like(x)
+    for f in range(frames):
+        xin = np.ascontiguousarray(x[perm][:, f * 160:(f + 1) * 160])
+        o = np.zeros_like(xin)
+        assert fn(hv, n, xin.ctypes.data_as(C.c_void_p), 160, o.ctypes.data_as(C.c_void_p), 160, 1) == 0
+        for i, p in enumerate(perm):
+            out[p, f * 160:(f + 1) * 160] = o[i]
+    b.close()
+    assert ref.any()
+    assert np.array_equal(ref, out)

@@ -3,6 +3,7 @@
 tag=${1:-rX}; O=gpurun_out/${tag}_matrix.log; : > $O
 run() { echo "== $*" >> $O; python bench.py "$@" 2>&1 | tail -1 >> $O; }
 run --steps 30 --warmup 3
+run() { echo "== $*" >> $O; python bench.py --no-tick "$@" 2>&1 | tail -1 >> $O; }
 run --steps 30 --warmup 3 --fixed
 run --steps 30 --warmup 3 --fixed --streams 8192
 run --steps 30 --warmup 3 --fixed --streams 8192 --fs 8000
