@@ -281,6 +281,24 @@ nsf_process_kernel(const NsfLaunch p) {
     if (SPLIT) bulk_load(X_noise, gS + kNsfOffAux, 4 * kNsfAuxStride * 4, barB);
   }
   bool state_ready = false;
+  // Prefetch across CTAs: the stream that the block scheduler will start in this warp's place about
+  // one wave from now (batch entry sidx + resident warps) gets its state and first frame pulled
+  // into L2, so that its own bulk copies find them there instead of in DRAM.  One wave of state is
+  // 17 MB of the 126 MB L2.
+  if (live && p.prefetch_ahead > 0 && sidx + p.prefetch_ahead < p.n_streams) {
+    const int an = sidx + p.prefetch_ahead;
+    const float* aS = p.state + (size_t)(p.slots ? p.slots[an] : p.slot_base + an) * kNsfStateWords;
+    if (lane == 0) {
+      bulk_prefetch_l2(aS, (kNsfOffHb + 96 * (NB - 1)) * 4);   // header | histories | overlap | high-band delay
+      bulk_prefetch_l2(aS + kNsfOffBins, kBinBytes);
+      if (SPLIT) bulk_prefetch_l2(aS + kNsfOffSplit, (96 + 4 * kNsfAuxStride) * 4);
+    }
+    if (p.frames > 0) {
+      const char* a = static_cast<const char*>(p.in) + (size_t)an * (size_t)p.in_stream_stride * (I16 ? 2 : 4);
+      const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(a) & 127u);
+      if (lane * 128u < mis + G::kFrame * (I16 ? 2u : 4u)) line_prefetch_l2(a - mis + 128 * lane);
+    }
+  }
 
   // PCM addressing: frame pair w of band b.
   const size_t in_base = (size_t)sidx * (size_t)p.in_stream_stride;

@@ -256,6 +256,22 @@ nsx_process_kernel(const NsxLaunch p) {
     bulk_load(RA, gS + kNsxOffRecA, kRecBytes, barB);
     bulk_load(RB, gS + kNsxOffRecB, kRecBytes, barB);
   }
+  // prefetch across CTAs (see nsf_kernel.cuh): state and first frame of the stream that will run in
+  // this warp's place about half a wave from now, into L2
+  if (live && p.prefetch_ahead > 0 && sidx + p.prefetch_ahead < p.n_streams) {
+    const int an = sidx + p.prefetch_ahead;
+    const uint32_t* aS = p.state + (size_t)(p.slots ? p.slots[an] : p.slot_base + an) * kNsxStateWords;
+    if (lane == 0) {
+      bulk_prefetch_l2(aS, (kNsxOffHb + 48 * (NB - 1)) * 4);   // header | histories | high-band delay
+      bulk_prefetch_l2(aS + kNsxOffRecA, kRecBytes);
+      bulk_prefetch_l2(aS + kNsxOffRecB, kRecBytes);
+    }
+    if (p.frames > 0) {
+      const char* a = reinterpret_cast<const char*>(static_cast<const int16_t*>(p.in) + (size_t)an * (size_t)p.in_stream_stride);
+      const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(a) & 127u);
+      if (lane * 128u < mis + (ANA == 256 ? 320u : 160u)) line_prefetch_l2(a - mis + 128 * lane);
+    }
+  }
 
   const int16_t* gin = static_cast<const int16_t*>(p.in) + (size_t)sidx * (size_t)p.in_stream_stride;
   int16_t* gout = static_cast<int16_t*>(p.out) + (size_t)sidx * (size_t)p.out_stream_stride;

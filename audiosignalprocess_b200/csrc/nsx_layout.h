@@ -76,6 +76,7 @@ struct NsxLaunch {
   uint32_t* state;
   const int* slots;        // [n_streams] slab index per batch entry; NULL: entry i sits in slot slot_base + i
   int slot_base = 0;
+  int prefetch_ahead = 0;  // > 0: a warp pulls the state of batch entry (its own + prefetch_ahead) into L2
   const NsxTables* tables;
   const void* in;   // int16 samples
   void* out;
