@@ -494,6 +494,7 @@ int LaunchNsfT(const NsfLaunch& p, cudaStream_t st) {
   // 1 / 2 resident waves ahead 127.0 / 122.9 / 120.8 / 119.8 / 120.6 / 122.9 / 131.0 us)
   q.prefetch_ahead = sms[dev & 63] * kNsfCtasPerSm * kNsfWarpsPerCta / 2;
   if (const char* e = getenv("NSB200_NSF_AHEAD")) q.prefetch_ahead = atoi(e);   // tuning: 0 = off
+  if (p.frames == 1 && !getenv("NSB200_NSF_NOWRAP")) q.prefetch_ahead = -q.prefetch_ahead;   // tick: wrap to the batch head
   const size_t smem = sizeof(float) * (kNsfCtaTableWords + kNsfWarpsPerCta * NsfWarpWords<SPLIT, NB>::value);
   if (smem > 48 * 1024)
     CU_OK(cudaFuncSetAttribute(nsf_process_kernel<ANA, NB, I16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -285,15 +285,19 @@ nsf_process_kernel(const NsfLaunch p) {
   // one wave from now (batch entry sidx + resident warps) gets its state and first frame pulled
   // into L2, so that its own bulk copies find them there instead of in DRAM.  One wave of state is
   // 17 MB of the 126 MB L2.
-  if (live && p.prefetch_ahead > 0 && sidx + p.prefetch_ahead < p.n_streams) {
-    const int an = sidx + p.prefetch_ahead;
+  // (prefetch_ahead < 0: a one-frame tick -- the entries past the end of the batch wrap around to its
+  // head, whose state this launch has already written back: the next tick's first wave starts warm)
+  const int ahead = p.prefetch_ahead < 0 ? -p.prefetch_ahead : p.prefetch_ahead;
+  const bool wrap = p.prefetch_ahead < 0 && sidx + ahead >= p.n_streams && sidx + ahead - p.n_streams < sidx;
+  if (live && ahead > 0 && (sidx + ahead < p.n_streams || wrap)) {
+    const int an = wrap ? sidx + ahead - p.n_streams : sidx + ahead;
     const float* aS = p.state + (size_t)(p.slots ? p.slots[an] : p.slot_base + an) * kNsfStateWords;
     if (lane == 0) {
       bulk_prefetch_l2(aS, (kNsfOffHb + 96 * (NB - 1)) * 4);   // header | histories | overlap | high-band delay
       bulk_prefetch_l2(aS + kNsfOffBins, kBinBytes);
       if (SPLIT) bulk_prefetch_l2(aS + kNsfOffSplit, (96 + 4 * kNsfAuxStride) * 4);
     }
-    if (p.frames > 0) {
+    if (p.frames > 0 && !wrap) {   // (the next tick's PCM is not this launch's to know)
       const char* a = static_cast<const char*>(p.in) + (size_t)an * (size_t)p.in_stream_stride * (I16 ? 2 : 4);
       const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(a) & 127u);
       if (lane * 128u < mis + G::kFrame * (I16 ? 2u : 4u)) line_prefetch_l2(a - mis + 128 * lane);

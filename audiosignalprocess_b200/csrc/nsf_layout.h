@@ -76,7 +76,7 @@ struct NsfLaunch {
   int* hist;               // cold histogram slab base
   const int* slots;        // [n_streams] slab index per batch entry; NULL: entry i sits in slot slot_base + i
   int slot_base = 0;
-  int prefetch_ahead = 0;  // > 0: a warp pulls the state of batch entry (its own + prefetch_ahead) into L2
+  int prefetch_ahead = 0;  // != 0: a warp pulls the state of batch entry (its own + |prefetch_ahead|) into L2; < 0: modulo the batch
   const NsfTables* tables;
   const void* in;          // int16 or float samples
   void* out;

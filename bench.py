@@ -492,8 +492,9 @@ def main():
         cpu = None
         if not a.no_cpu:
             cores = os.cpu_count() or 1
-            # ~15-25 s of CPU work: 8 streams per core, 60 s of audio each (the configuration's duration)
-            streams = cores * 8
+            # ~15-25 core-seconds of CPU work: 24 streams per core, 60 s of audio each (the configuration's
+            # duration); the reference runs ~900 audio-s/s per core on the box's hosts
+            streams = cores * 24
             frames = 6000 if a.fs <= 16000 else 2000
             v = cpu_reference_run(kind, a.fs, a.mode, streams, frames, cores)
             if v is not None:
