@@ -44,6 +44,12 @@ inline void nsf_fill_tables(Tables* t) {
   t->tw[64].x = 0.f;  t->tw[64].y = 1.f;
   t->tw[128].x = -1.f; t->tw[128].y = 0.f;
   t->tw[192].x = 0.f; t->tw[192].y = -1.f;
+  // the eighth roots the warp FFT's last pass writes out by hand (ns_warp.cuh): one constant
+  const float c8 = (float)cos(kPi / 4.0);
+  t->tw[32].x = c8;   t->tw[32].y = c8;
+  t->tw[96].x = -c8;  t->tw[96].y = c8;
+  t->tw[160].x = -c8; t->tw[160].y = -c8;
+  t->tw[224].x = c8;  t->tw[224].y = -c8;
   for (int i = 1; i < 132; ++i) t->logi[i] = (float)log((double)(float)i);
   // sequential float sums exactly as ns_core.c:1088-1100 accumulates them
   for (int v = 0; v < 2; ++v) {
