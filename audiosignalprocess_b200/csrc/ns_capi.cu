@@ -1346,7 +1346,10 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
       // nsb_sqrtf_p1 == sqrtf + 1 on [0, 2^70): squared spectral magnitudes incl. the tiny end
       const float x = __uint_as_float((h2 & 0x007fffffu) | (((h1 >> 7) % 140u + 57u) << 23));
       if (__float_as_uint(nsb_sqrtf_p1(x)) != __float_as_uint(__fadd_rn(__fsqrt_rn(x), 1.f))) ++mism;
+      // nsb_sqrtf == sqrtf on [2^-49, 2^70) (energy ratios); 0 below 2^-50 by design
+      if (x >= 1.7763568394002505e-15f && __float_as_uint(nsb_sqrtf(x)) != __float_as_uint(__fsqrt_rn(x))) ++mism;
       const float xs = __uint_as_float(h1 & 0x00ffffffu);   // subnormals and the smallest normals
+      if (nsb_sqrtf(xs) != 0.f || nsb_sqrtf(0.f) != 0.f) ++mism;
       if (nsb_sqrtf_p1(xs) != 1.f || nsb_sqrtf_p1(0.f) != 1.f) ++mism;
     }
     const float c = (float)(h1 % 401u);   // small integers as in counters

@@ -80,8 +80,15 @@ NSB_DEV float sat_s16f(float v) {  // WEBRTC_SPL_SAT(32767, v, -32768)
 NSB_DEV int round_s16(float v) {  // FloatS16ToS16, common_audio/include/audio_util.h:41-49
   // v > 0 ? (v >= 32766.5 ? 32767 : (int)(v + .5)) : (v <= -32767.5 ? -32768 : (int)(v - .5));
   // v -+ 0.5 is exact below 2^15, so truncating first and clamping after gives the same integers.
+#ifdef __CUDA_ARCH__
+  // float -> s16 conversion truncates and clamps in one instruction (checked by the device self-test)
+  short r;
+  asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(v + copysignf(0.5f, v)));
+  return (int)r;
+#else
   const int r = (int)(v + copysignf(0.5f, v));
   return r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
+#endif
 }
 
 // One 32-bit-lane PCM word as it sits in memory: two int16 samples, or a float pair.
@@ -1000,7 +1007,7 @@ nsf_process_kernel(const NsfLaunch p) {
       if (gainmap == 1 && blockInd > 200) {
         energy2 = warp_sum(energy2);
         float factor1 = 1.f, factor2 = 1.f;
-        float gain = sqrtf(energy2 / (energy1 + 1.f));
+        float gain = nsb_sqrtf(fdiv(energy2, energy1 + 1.f));   // branch-free forms: ns_warp.cuh
         if (gain > 0.5f) {
           factor1 = 1.f + 1.3f * (gain - 0.5f);
           if (gain * factor1 > 1.f) factor1 = 1.f / gain;
