@@ -207,7 +207,7 @@ nsx_process_kernel(const NsxLaunch p) {
   int16_t* s_logf = reinterpret_cast<int16_t*>(smem + 256);
 
   const int lane = lane_id();
-  const int warp = (int)(threadIdx.x >> 5);
+  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: see nsf_kernel.cuh
   const NsxTables* T = p.tables;
   const int warps_per_cta = (int)(blockDim.x >> 5);
   const int sidx = (int)blockIdx.x * warps_per_cta + warp;
@@ -238,7 +238,7 @@ nsx_process_kernel(const NsxLaunch p) {
     mbar_arrive_expect(barT, sizeof(uint32_t) * kNsxTableImgWords);
     bulk_load(smem, T->img[ANA == 256 ? 0 : 1], sizeof(uint32_t) * kNsxTableImgWords, barT);
   }
-  const int slot = live ? (p.slots ? p.slots[sidx] : p.slot_base + sidx) : 0;
+  const int slot = __shfl_sync(kFullMask, live ? (p.slots ? p.slots[sidx] : p.slot_base + sidx) : 0, 0);
   uint32_t* gS = p.state + (size_t)slot * kNsxStateWords;
   int* gHist = reinterpret_cast<int*>(gS + kNsxOffHist);
   uint32_t* gInit = gS + kNsxOffInitMagn;
