@@ -12,7 +12,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -28,13 +31,20 @@
 namespace nsb200 {
 namespace {
 
-std::mutex g_mu;
-std::string g_err;
-uint64_t g_launches = 0;
-int g_create_device = -1;
+// Threading.  The reference keeps no global state at all (ns/noise_suppression.c:20-66: every call works on
+// its own handle), so independent handles may be driven from independent threads.  Here handles share per-GPU
+// slabs, streams and staging buffers, so the rule is per device: calls that only USE devices (every batch /
+// process / getter call) hold g_rw shared plus the mutex of each device they touch -- two host threads driving
+// two GPUs run concurrently, GPU waits included -- and calls that change what handles exist or where they live
+// (Create, Free, Init, migration, state import) hold g_rw exclusively.  The last error, the device new handles
+// are created on and the validated-handle-list memo are per thread.
+std::shared_mutex g_rw;
+thread_local std::string t_err;
+std::atomic<uint64_t> g_launches{0};
+thread_local int t_create_device = -1;
 
 int Fail(const std::string& m) {
-  g_err = m;
+  t_err = m;
   return -1;
 }
 #define CU_OK(call)                                                              \
@@ -56,6 +66,7 @@ struct Handle {
   int init_flag;
   bool analyze_seen;
   float analyze_frame[160];
+  uint64_t seen_stamp;   // batch validation: the call that last listed this handle (duplicates race on one slab)
   bool split_mode;   // float NS: the stream has been fed distinct Analyze / Process signals (sticky)
   double down_vsi;   // 48 kHz: running position of the 640 -> 480 resampler (band_host_init.h)
 };
@@ -70,8 +81,10 @@ struct SlabPool {
 };
 
 struct DeviceCtx {
+  std::mutex mu;                      // held by every call that uses this device (see "Threading")
   int dev = -1;
   bool ready = false;
+  cudaEvent_t user_done = nullptr;    // last launch a *Device entry point enqueued on a caller's stream
   cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
   NsfTables* d_nsf_tables = nullptr;
   NsxTables* d_nsx_tables = nullptr;
@@ -110,15 +123,28 @@ struct DeviceCtx {
   std::vector<cudaEvent_t> band_events;
 };
 
-std::vector<DeviceCtx> g_devs;
+// (DeviceCtx holds a mutex: a fixed array, sized once)
+struct DeviceList {
+  std::unique_ptr<DeviceCtx[]> p;
+  int n = 0;
+  size_t size() const { return (size_t)n; }
+  bool empty() const { return n == 0; }
+  DeviceCtx& operator[](size_t i) { return p[i]; }
+  DeviceCtx* begin() { return p.get(); }
+  DeviceCtx* end() { return p.get() + n; }
+};
+DeviceList g_devs;
+std::once_flag g_devs_once;
 
 // Asynchronous host-pointer batches (WebRtcNs[x]_ProcessBatchAsync) still in flight: ticket ->
-// one completion event per device.  Every other entry point drains them first (ApiLock), so the
-// rest of the library keeps its "nothing of mine is running" assumption.
+// one completion event per device.  Every other call that uses a device first waits for the tickets that
+// involve it (UseLock::Device), so the rest of the library keeps its "nothing of mine is running on this
+// device" assumption.
 struct PendingBatch {
   uint64_t ticket;
   std::vector<std::pair<int, cudaEvent_t>> done;
 };
+std::mutex g_pend_mu;
 std::vector<PendingBatch> g_pending;
 uint64_t g_next_ticket = 1;
 
@@ -130,31 +156,72 @@ void FinishPending(PendingBatch& p) {
   }
   p.done.clear();
 }
-void DrainPendingLocked() {
-  for (PendingBatch& p : g_pending) FinishPending(p);
-  g_pending.clear();
+// dev < 0: every ticket
+void DrainPending(int dev) {
+  std::vector<PendingBatch> mine;
+  {
+    std::lock_guard<std::mutex> g(g_pend_mu);
+    for (size_t i = 0; i < g_pending.size();) {
+      bool hit = dev < 0;
+      for (auto& de : g_pending[i].done) hit = hit || de.first == dev;
+      if (hit) {
+        mine.push_back(std::move(g_pending[i]));
+        g_pending.erase(g_pending.begin() + (long)i);
+      } else {
+        ++i;
+      }
+    }
+  }
+  for (PendingBatch& p : mine) FinishPending(p);
 }
-// true between CheckBatch and the end of the API call: the call's handle list IS g_memo.hs, so the
+// true between CheckBatch and the end of the API call: the call's handle list IS t_memo.hs, so the
 // helpers below need not compare 8 bytes per stream again (a one-frame tick over 32768 streams is
 // ~125 us of GPU time; the host side of the call has to stay well below that)
-bool g_call_is_memo = false;
-struct ApiLock {
-  std::lock_guard<std::mutex> guard;
-  explicit ApiLock(bool drain = true) : guard(g_mu) {
-    g_call_is_memo = false;
-    if (drain && !g_pending.empty()) DrainPendingLocked();
+thread_local bool t_call_is_memo = false;
+// Changes which handles exist or where they live: alone in the library, nothing in flight.
+struct ExclusiveLock {
+  std::unique_lock<std::shared_mutex> guard;
+  ExclusiveLock() : guard(g_rw) {
+    t_call_is_memo = false;
+    DrainPending(-1);
   }
+};
+// Uses devices: shared with other users, one mutex per device touched (taken in ascending device order
+// when a call spans several).
+struct UseLock {
+  std::shared_lock<std::shared_mutex> guard;
+  std::vector<std::unique_lock<std::mutex>> held;
+  UseLock() : guard(g_rw) { t_call_is_memo = false; }
+  void Device(int dev, bool drain = true);
 };
 
 int EnsureDevices() {
-  if (!g_devs.empty()) return 0;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0)
-    return Fail(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
-  g_devs.resize(n);
-  for (int i = 0; i < n; ++i) g_devs[i].dev = i;
+  std::call_once(g_devs_once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      t_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+      return;
+    }
+    g_devs.p.reset(new DeviceCtx[n]);
+    g_devs.n = n;
+    for (int i = 0; i < n; ++i) g_devs[i].dev = i;
+  });
+  if (g_devs.empty()) {
+    if (t_err.empty() || t_err.compare(0, 14, "no CUDA device") != 0) {
+      int n = 0;
+      cudaError_t e = cudaGetDeviceCount(&n);
+      return Fail(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
+    }
+    return -1;
+  }
   return 0;
+}
+
+void UseLock::Device(int dev, bool drain) {
+  if (EnsureDevices() != 0 || dev < 0 || dev >= (int)g_devs.size()) return;   // DeviceReady reports it
+  held.emplace_back(g_devs[dev].mu);
+  if (drain) DrainPending(dev);
 }
 
 int PoolGrow(DeviceCtx& d, SlabPool& p, int want) {
@@ -243,7 +310,8 @@ int DeviceReady(int dev, DeviceCtx** out) {
 // tens of thousands of handles per call: the last validated list is remembered, and anything that
 // could invalidate it (Create / Free / Init / migration / import / a stream turning two-signal)
 // bumps g_epoch.  Measured at 32 768 streams: ~340 us of host work per call against a 220 us kernel.
-uint64_t g_epoch = 1;
+std::atomic<uint64_t> g_epoch{1};
+std::atomic<uint64_t> g_call_stamp{1};
 struct BatchMemo {
   uint64_t epoch = 0;
   uint32_t magic = 0;
@@ -253,7 +321,7 @@ struct BatchMemo {
   bool any_split = false;       // some handle of `hs` is in two-signal mode
   int single_dev = -1;          // the device all of `hs` live on, -1 if they span several
 };
-BatchMemo g_memo;
+thread_local BatchMemo t_memo;   // per calling thread: the list that thread ticks
 
 Handle* AsHandle(void* h, uint32_t magic) {
   Handle* p = static_cast<Handle*>(h);
@@ -309,11 +377,11 @@ int UploadSlots(DeviceCtx& d, const std::vector<int>& slots, cudaStream_t st) {
 }
 
 int Create(void** out, uint32_t magic) {
-  ApiLock lk;
+  ExclusiveLock lk;
   ++g_epoch;   // handle lists validated so far are stale (BatchMemo)
   if (!out) return Fail("NULL handle pointer");
   *out = nullptr;
-  int dev = g_create_device;
+  int dev = t_create_device;
   if (dev < 0) {
     if (EnsureDevices() != 0) return -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return Fail("cudaGetDevice failed");
@@ -345,7 +413,7 @@ int Create(void** out, uint32_t magic) {
 }
 
 int Free(void* hv, uint32_t magic) {
-  ApiLock lk;
+  ExclusiveLock lk;
   ++g_epoch;   // handle lists validated so far are stale (BatchMemo)
   Handle* h = AsHandle(hv, magic);
   if (!h) return 0;  // reference: free(NULL) is fine, returns 0
@@ -364,7 +432,7 @@ int Free(void* hv, uint32_t magic) {
 int BandSlot(const Handle* h) { return h->magic == kMagicF ? 2 * h->slot : 2 * h->slot + 1; }
 
 int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
-  ApiLock lk;
+  ExclusiveLock lk;
   ++g_epoch;   // handle lists validated so far are stale (BatchMemo)
   if (!hv || n <= 0) return Fail("no handles");
   if (!(fs == 8000 || fs == 16000 || fs == 32000 || fs == 48000)) return Fail("unsupported fs");
@@ -441,10 +509,11 @@ int InitMany(void* const* hv, int n, uint32_t fs, int mode, uint32_t magic) {
 int SetPolicy(void* hv, int mode, uint32_t magic) {
   Handle* h;
   {
-    ApiLock lk;
+    UseLock lk;
     h = AsHandle(hv, magic);
     if (!h) return Fail("bad handle");
     if (mode < 0 || mode > 3) return Fail("mode out of range");
+    lk.Device(h->dev);
     if (!h->init_flag) {
       // the reference only writes fields of the struct here; Init later resets
       // them to mode 0, so this is a no-op before Init.
@@ -520,12 +589,12 @@ int LaunchNsf(int ana, int nb, bool i16, bool split, const NsfLaunch& p, cudaStr
 // histories and magnitude memories differ, so later fused calls on it run the split kernel with
 // the Process signal fed to both (identical results to the reference either way).
 bool SameAsMemo(const std::vector<Handle*>& hs) {
-  if (g_call_is_memo && g_memo.epoch == g_epoch && g_memo.hs.size() == hs.size()) return true;
-  return g_memo.epoch == g_epoch && g_memo.hs.size() == hs.size() &&
-         memcmp(g_memo.hs.data(), hs.data(), sizeof(Handle*) * hs.size()) == 0;
+  if (t_call_is_memo && t_memo.epoch == g_epoch && t_memo.hs.size() == hs.size()) return true;
+  return t_memo.epoch == g_epoch && t_memo.hs.size() == hs.size() &&
+         memcmp(t_memo.hs.data(), hs.data(), sizeof(Handle*) * hs.size()) == 0;
 }
 bool NeedSplit(std::vector<Handle*>& hs, bool split_call) {
-  if (!split_call && SameAsMemo(hs) && !g_memo.any_split) return false;   // validated list, all fused
+  if (!split_call && SameAsMemo(hs) && !t_memo.any_split) return false;   // validated list, all fused
   bool split = split_call;
   for (Handle* h : hs) split = split || h->split_mode;
   if (split) {
@@ -577,11 +646,14 @@ int NumBands(uint32_t fs) { return fs == 32000 ? 2 : (fs == 48000 ? 3 : 1); }
 
 // Host buffers of a host-pointer batch call at 32/48 kHz: the copies become the first and last
 // stage of the band pipeline below.
+struct HostSub { int first, count, row; };   // batch entries [first, first + count) = staging rows [row, row + count)
 struct HostIo {
-  const int16_t* in;
+  const int16_t* in;     // the caller's buffers: entry i at in + i * in_stride
   size_t in_stride;
   int16_t* out;
   size_t out_stride;
+  const HostSub* subs;   // which entries this device's staging rows hold
+  int nsubs;
 };
 
 constexpr int kBandMaxStages = 9;        // copy-in | 7 band / NS stages | copy-out
@@ -781,13 +853,19 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
       if (k > 0) CU_OK(cudaStreamWaitEvent(s, d.band_events[(size_t)c * nstages + k - 1], 0));
       const int bk = k - first;   // band stage index
       if (bk < 0) {
-        CU_OK(cudaMemcpy2DAsync(const_cast<int16_t*>(d_in) + (size_t)f0 * fl, in_stride * sizeof(int16_t),
-                                host->in + (size_t)f0 * fl, host->in_stride * sizeof(int16_t),
-                                (size_t)nf * fl * sizeof(int16_t), n, cudaMemcpyHostToDevice, s));
+        for (int u = 0; u < host->nsubs; ++u) {
+          const HostSub& sb = host->subs[u];
+          CU_OK(cudaMemcpy2DAsync(const_cast<int16_t*>(d_in) + (size_t)sb.row * in_stride + (size_t)f0 * fl, in_stride * sizeof(int16_t),
+                                  host->in + (size_t)sb.first * host->in_stride + (size_t)f0 * fl, host->in_stride * sizeof(int16_t),
+                                  (size_t)nf * fl * sizeof(int16_t), sb.count, cudaMemcpyHostToDevice, s));
+        }
       } else if (bk == band_stages) {
-        CU_OK(cudaMemcpy2DAsync(host->out + (size_t)f0 * fl, host->out_stride * sizeof(int16_t),
-                                d_out + (size_t)f0 * fl, out_stride * sizeof(int16_t),
-                                (size_t)nf * fl * sizeof(int16_t), n, cudaMemcpyDeviceToHost, s));
+        for (int u = 0; u < host->nsubs; ++u) {
+          const HostSub& sb = host->subs[u];
+          CU_OK(cudaMemcpy2DAsync(host->out + (size_t)sb.first * host->out_stride + (size_t)f0 * fl, host->out_stride * sizeof(int16_t),
+                                  d_out + (size_t)sb.row * out_stride + (size_t)f0 * fl, out_stride * sizeof(int16_t),
+                                  (size_t)nf * fl * sizeof(int16_t), sb.count, cudaMemcpyDeviceToHost, s));
+        }
       } else if (bk == ns_stage) {
         if (LaunchNs(d, magic, ana, nb, n, d.d_bands, bands_ss, d.d_bands, bands_ss, nb * 160, 160, f0, nf, s, split) != 0)
           return -1;
@@ -830,15 +908,15 @@ int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int1
   // slot lists: [0,n) = NS slots, [n,2n) = band slots (remembered for the validated list)
   const bool memo = SameAsMemo(hs);
   std::vector<int> built;
-  if (!memo || g_memo.slots.empty()) {
+  if (!memo || t_memo.slots.empty()) {
     built.resize(nb > 1 ? 2 * (size_t)n : (size_t)n);
     for (int i = 0; i < n; ++i) {
       built[i] = hs[i]->slot;
       if (nb > 1) built[n + i] = BandSlot(hs[i]);
     }
-    if (memo) g_memo.slots = built;
+    if (memo) t_memo.slots = built;
   }
-  const std::vector<int>& all = (memo && !g_memo.slots.empty()) ? g_memo.slots : built;
+  const std::vector<int>& all = (memo && !t_memo.slots.empty()) ? t_memo.slots : built;
   if (UploadSlots(d, all, st) != 0) return -1;
   if (d_ana && (magic != kMagicF || nb != 1))
     return Fail("a separate Analyze signal is supported for the float suppressor on full-band PCM at 8/16 kHz "
@@ -863,107 +941,153 @@ int RunDevice(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const int1
   return 0;
 }
 
-int CheckBatch(void* const* hv, int n, uint32_t magic, size_t in_stride, size_t out_stride,
-               int frames, std::vector<Handle*>* hs) {
+// Validates a batch call.  in / out (may be NULL for calls that carry no PCM): the kernels move PCM as 32-bit
+// words (16-byte vectors at 32/48 kHz), so the pointers must be aligned to that; strides likewise.  A handle
+// listed twice would put two warps on one state slab.  With one stream the stride is never used to step.
+int CheckBatch(void* const* hv, int n, uint32_t magic, size_t* in_stride, size_t* out_stride,
+               int frames, std::vector<Handle*>* hs, const void* in = nullptr, const void* out = nullptr) {
   if (!hv || n <= 0) return Fail("no handles");
   if (frames < 0) return Fail("negative frame count");
-  if ((in_stride | out_stride) & 1) return Fail("strides must be even");
-  if (g_memo.epoch == g_epoch && g_memo.magic == magic && g_memo.hv.size() == (size_t)n &&
-      memcmp(g_memo.hv.data(), hv, sizeof(void*) * (size_t)n) == 0) {
-    *hs = g_memo.hs;
+  if ((*in_stride | *out_stride) & 1) return Fail("strides must be even");
+  if (t_memo.epoch == g_epoch && t_memo.magic == magic && t_memo.hv.size() == (size_t)n &&
+      memcmp(t_memo.hv.data(), hv, sizeof(void*) * (size_t)n) == 0) {
+    *hs = t_memo.hs;
   } else {
     hs->resize(n);
     bool any_split = false;
     int single_dev = -1;
+    const uint64_t stamp = ++g_call_stamp;
     for (int i = 0; i < n; ++i) {
       Handle* h = AsHandle(hv[i], magic);
       if (!h) return Fail("bad handle in batch");
       if (!h->init_flag) return Fail("handle not initialised");
       if (h->fs != static_cast<Handle*>(hv[0])->fs) return Fail("mixed sample rates in one batch");
+      if (h->seen_stamp == stamp) return Fail("handle listed twice in one batch");
+      h->seen_stamp = stamp;
       any_split = any_split || h->split_mode;
       single_dev = i == 0 ? h->dev : (single_dev == h->dev ? single_dev : -1);
       (*hs)[i] = h;
     }
-    g_memo.epoch = g_epoch;
-    g_memo.magic = magic;
-    g_memo.hv.assign(hv, hv + n);
-    g_memo.hs = *hs;
-    g_memo.slots.clear();
-    g_memo.any_split = any_split;
-    g_memo.single_dev = single_dev;
+    t_memo.epoch = g_epoch;
+    t_memo.magic = magic;
+    t_memo.hv.assign(hv, hv + n);
+    t_memo.hs = *hs;
+    t_memo.slots.clear();
+    t_memo.any_split = any_split;
+    t_memo.single_dev = single_dev;
   }
-  const size_t need = (size_t)frames * ((*hs)[0]->fs / 100);
-  if (n > 1 && (in_stride < need || out_stride < need)) return Fail("stride shorter than the frames of one stream");
-  g_call_is_memo = true;
+  const uint32_t fs = (*hs)[0]->fs;
+  const size_t need = (size_t)frames * (fs / 100);
+  if (n == 1) {   // one row: any stride will do, and a 2-D copy must not see a pitch below its width
+    if (*in_stride < need) *in_stride = need;
+    if (*out_stride < need) *out_stride = need;
+  } else if (*in_stride < need || *out_stride < need) {
+    return Fail("stride shorter than the frames of one stream");
+  }
+  const uintptr_t align = fs > 16000 ? 15u : 3u;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & align)
+    return Fail(fs > 16000 ? "PCM pointers must be 16-byte aligned at 32/48 kHz" : "PCM pointers must be 4-byte aligned");
+  t_call_is_memo = true;
+  return 0;
+}
+
+// A launch a *Device entry point put on the caller's stream: the library's own stream (and with it every
+// later call that synchronises or enqueues there: Free, Init, set_policy, the getter, host-pointer batches)
+// is ordered behind it.
+int OrderAfterUserStream(DeviceCtx& d, cudaStream_t st) {
+  if (st == d.stream) return 0;
+  if (!d.user_done) CU_OK(cudaEventCreateWithFlags(&d.user_done, cudaEventDisableTiming));
+  CU_OK(cudaEventRecord(d.user_done, st));
+  CU_OK(cudaStreamWaitEvent(d.stream, d.user_done, 0));
   return 0;
 }
 
 int BatchDevice(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
                 int16_t* out, size_t out_stride, int frames, void* stream) {
-  ApiLock lk;
-  static std::vector<Handle*> hs;   // (under the API lock) keeps its capacity: no 256 KB allocation per tick
-  if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
+  UseLock lk;
+  static thread_local std::vector<Handle*> hs;   // keeps its capacity: no 256 KB allocation per tick
+  if (CheckBatch(hv, n, magic, &in_stride, &out_stride, frames, &hs, in, out) != 0) return -1;
   if (frames == 0) return 0;
-  if (g_memo.single_dev < 0) return Fail("device batch spans several GPUs");
+  if (t_memo.single_dev < 0) return Fail("device batch spans several GPUs");
+  lk.Device(hs[0]->dev);
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
-  return RunDevice(*d, magic, hs, in, in_stride, out, out_stride, frames, st);
+  if (RunDevice(*d, magic, hs, in, in_stride, out, out_stride, frames, st) != 0) return -1;
+  return OrderAfterUserStream(*d, st);
 }
 
-// Host-pointer batch: bucket by device; per device copy in -> run -> copy out.
-// Frames are cut into chunks so that the H2D copy of chunk c+1 and the D2H copy
-// of chunk c-1 overlap the kernel of chunk c (three streams, events).
+// Host-pointer batch: the handles are bucketed by device (any order, any interleaving of devices in the
+// list); per device copy in -> run -> copy out.  Frames are cut into chunks so that the H2D copy of chunk
+// c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c (three streams, events).
+// A bucket's streams sit in its staging buffers in batch order; runs of consecutive batch entries move with
+// one 2-D copy each.
+struct HostBucket {
+  int dev = -1;
+  std::vector<HostSub> subs;
+  std::vector<Handle*> hs;
+};
+
 int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t in_stride,
               int16_t* out, size_t out_stride, int frames, uint64_t* ticket = nullptr) {
   // ticket: asynchronous call -- everything is enqueued behind what earlier asynchronous calls
   // left in the three queues and the call returns without waiting (0 = nothing to wait for)
-  ApiLock lk(ticket == nullptr);
+  UseLock lk;
   if (ticket) *ticket = 0;
   std::vector<Handle*> hs;
-  if (CheckBatch(hv, n, magic, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (CheckBatch(hv, n, magic, &in_stride, &out_stride, frames, &hs, in, out) != 0) return -1;
   if (frames == 0) return 0;
   const int fl = (int)hs[0]->fs / 100;
-  // contiguous runs of batch indices that live on one device
-  struct Run { int dev, first, count; };
-  std::vector<Run> runs;
-  for (int i = 0; i < n; ++i) {
-    if (!runs.empty() && runs.back().dev == hs[i]->dev) runs.back().count++;
-    else runs.push_back(Run{hs[i]->dev, i, 1});
+  std::vector<HostBucket> buckets;
+  {
+    std::vector<int> of_dev(g_devs.size(), -1);
+    for (int i = 0; i < n; ++i) {
+      const int dv = hs[i]->dev;
+      if (of_dev[dv] < 0) {
+        of_dev[dv] = (int)buckets.size();
+        buckets.emplace_back();
+        buckets.back().dev = dv;
+      }
+      HostBucket& b = buckets[of_dev[dv]];
+      if (!b.subs.empty() && b.subs.back().first + b.subs.back().count == i) b.subs.back().count++;
+      else b.subs.push_back(HostSub{i, 1, (int)b.hs.size()});
+      b.hs.push_back(hs[i]);
+    }
+    std::sort(buckets.begin(), buckets.end(), [](const HostBucket& x, const HostBucket& y) { return x.dev < y.dev; });
   }
-  if (NumBands(hs[0]->fs) > 1) {
-    // (asynchronous calls: this path blocks, after whatever is still in flight)
-    if (ticket && !g_pending.empty()) DrainPendingLocked();
+  const bool bands = NumBands(hs[0]->fs) > 1;
+  // (asynchronous calls at 32/48 kHz: that path blocks, after whatever is still in flight)
+  for (const HostBucket& b : buckets) lk.Device(b.dev, ticket == nullptr || bands);
+  if (bands) {
     // 32/48 kHz: the copies are the first and last stage of the band pipeline (RunBandBlock);
     // staging holds one block of frames per direction
     const int block = frames < kBandBlockFrames ? frames : kBandBlockFrames;
-    for (const Run& r : runs) {
+    for (const HostBucket& b : buckets) {
       DeviceCtx* d;
-      if (DeviceReady(r.dev, &d) != 0) return -1;
-      const size_t need = (size_t)r.count * block * fl;
+      if (DeviceReady(b.dev, &d) != 0) return -1;
+      const size_t need = b.hs.size() * (size_t)block * fl;
       if (need > d->stage_elems) {
         CU_OK(cudaDeviceSynchronize());
         if (d->d_in) { CU_OK(cudaFree(d->d_in)); CU_OK(cudaFree(d->d_out)); }
         CU_OK(cudaMalloc(&d->d_in, sizeof(int16_t) * need));
         CU_OK(cudaMalloc(&d->d_out, sizeof(int16_t) * need));
         d->stage_elems = need;
+        d->pipe_per = 0;
       }
     }
     for (int f0 = 0; f0 < frames; f0 += block) {
       const int nf = frames - f0 < block ? frames - f0 : block;
-      for (const Run& r : runs) {
-        DeviceCtx* d = &g_devs[r.dev];
-        CU_OK(cudaSetDevice(r.dev));
-        std::vector<Handle*> sub(hs.begin() + r.first, hs.begin() + r.first + r.count);
-        HostIo hio = {in + (size_t)r.first * in_stride + (size_t)f0 * fl, in_stride,
-                      out + (size_t)r.first * out_stride + (size_t)f0 * fl, out_stride};
+      for (HostBucket& b : buckets) {
+        DeviceCtx* d = &g_devs[b.dev];
+        CU_OK(cudaSetDevice(b.dev));
+        HostIo hio = {in + (size_t)f0 * fl, in_stride, out + (size_t)f0 * fl, out_stride, b.subs.data(), (int)b.subs.size()};
         const size_t per = (size_t)block * fl;
-        if (RunDevice(*d, magic, sub, d->d_in, per, d->d_out, per, nf, d->stream, &hio) != 0) return -1;
+        if (RunDevice(*d, magic, b.hs, d->d_in, per, d->d_out, per, nf, d->stream, &hio) != 0) return -1;
       }
     }
-    for (const Run& r : runs) {
-      CU_OK(cudaSetDevice(r.dev));
-      CU_OK(cudaStreamSynchronize(g_devs[r.dev].stream));
+    for (const HostBucket& b : buckets) {
+      CU_OK(cudaSetDevice(b.dev));
+      CU_OK(cudaStreamSynchronize(g_devs[b.dev].stream));
     }
     return 0;
   }
@@ -1010,11 +1134,12 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
     const int v = atoi(e);
     if (v >= 2 && v <= 8) kBuf = v;
   }
-  for (const Run& r : runs) {
+  for (const HostBucket& b : buckets) {
     DeviceCtx* d;
-    if (DeviceReady(r.dev, &d) != 0) return -1;
+    if (DeviceReady(b.dev, &d) != 0) return -1;
+    const int count = (int)b.hs.size();
     const size_t per = (size_t)chunk * fl;           // samples per stream per chunk
-    const size_t need = kBuf * (size_t)r.count * per;
+    const size_t need = kBuf * (size_t)count * per;
     if (need > d->stage_elems) {
       CU_OK(cudaDeviceSynchronize());
       if (d->d_in) { CU_OK(cudaFree(d->d_in)); CU_OK(cudaFree(d->d_out)); }
@@ -1023,20 +1148,20 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
       d->stage_elems = need;
       d->pipe_per = 0;
     }
-    if (d->pipe_per != per || d->pipe_count != r.count || d->pipe_bufs != kBuf) {
+    if (d->pipe_per != per || d->pipe_count != count || d->pipe_bufs != kBuf) {
       // the buffers are cut differently from the pipeline still in flight: let it run dry
       CU_OK(cudaStreamSynchronize(d->copy_in));
       CU_OK(cudaStreamSynchronize(d->stream));
       CU_OK(cudaStreamSynchronize(d->copy_out));
       d->pipe_per = per;
-      d->pipe_count = r.count;
+      d->pipe_count = count;
       d->pipe_bufs = kBuf;
-      for (int b = 0; b < kBuf; ++b) d->pipe_used[b] = false;
+      for (int k = 0; k < kBuf; ++k) d->pipe_used[k] = false;
     }
-    for (int b = 0; b < kBuf; ++b)
-      if (!d->pipe_kdone[b]) {
-        CU_OK(cudaEventCreateWithFlags(&d->pipe_kdone[b], cudaEventDisableTiming));
-        CU_OK(cudaEventCreateWithFlags(&d->pipe_drained[b], cudaEventDisableTiming));
+    for (int k = 0; k < kBuf; ++k)
+      if (!d->pipe_kdone[k]) {
+        CU_OK(cudaEventCreateWithFlags(&d->pipe_kdone[k], cudaEventDisableTiming));
+        CU_OK(cudaEventCreateWithFlags(&d->pipe_drained[k], cudaEventDisableTiming));
       }
     const size_t nev = 3 * (size_t)nchunks;
     while (d->events.size() < nev) {
@@ -1047,54 +1172,55 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   }
   // One device at a time issues its whole pipeline asynchronously; devices run
   // concurrently because nothing below blocks the host until the final syncs.
-  for (size_t ri = 0; ri < runs.size(); ++ri) {
-    const Run& r = runs[ri];
-    DeviceCtx* d = &g_devs[r.dev];
-    CU_OK(cudaSetDevice(r.dev));
-    std::vector<Handle*> sub(hs.begin() + r.first, hs.begin() + r.first + r.count);
+  for (HostBucket& b : buckets) {
+    DeviceCtx* d = &g_devs[b.dev];
+    CU_OK(cudaSetDevice(b.dev));
+    const int count = (int)b.hs.size();
     const size_t per = (size_t)chunk * fl;
     std::vector<cudaEvent_t>& ev = d->events;
     // NSB200_TRACE=1: per-chunk timeline of the three queues on stderr (tuning aid)
     const bool trace = getenv("NSB200_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
-    auto mark = [&](cudaStream_t s) {
+    auto mark = [&](cudaStream_t st) {
       if (!trace) return;
       cudaEvent_t e;
       cudaEventCreate(&e);
-      cudaEventRecord(e, s);
+      cudaEventRecord(e, st);
       tev.push_back(e);
     };
     for (int c = 0; c < nchunks; ++c) {
       const int f0 = starts[c];
       const int nf = starts[c + 1] - f0;
-      const int b = (int)((d->pipe_seq + (unsigned long long)c) % (unsigned long long)kBuf);
-      int16_t* din = d->d_in + (size_t)b * r.count * per;
-      int16_t* dout = d->d_out + (size_t)b * r.count * per;
-      // buffer b was last read by the kernel three chunks back and last drained by its copy-out
+      const int k = (int)((d->pipe_seq + (unsigned long long)c) % (unsigned long long)kBuf);
+      int16_t* din = d->d_in + (size_t)k * count * per;
+      int16_t* dout = d->d_out + (size_t)k * count * per;
+      // buffer k was last read by the kernel three chunks back and last drained by its copy-out
       // (of this call or, for asynchronous calls, of the one before)
-      if (d->pipe_used[b]) {
-        CU_OK(cudaStreamWaitEvent(d->copy_in, d->pipe_kdone[b], 0));
-        CU_OK(cudaStreamWaitEvent(d->stream, d->pipe_drained[b], 0));
+      if (d->pipe_used[k]) {
+        CU_OK(cudaStreamWaitEvent(d->copy_in, d->pipe_kdone[k], 0));
+        CU_OK(cudaStreamWaitEvent(d->stream, d->pipe_drained[k], 0));
       }
       mark(d->copy_in);
-      CU_OK(cudaMemcpy2DAsync(din, per * sizeof(int16_t), in + (size_t)r.first * in_stride + (size_t)f0 * fl,
-                              in_stride * sizeof(int16_t), (size_t)nf * fl * sizeof(int16_t), r.count,
-                              cudaMemcpyHostToDevice, d->copy_in));
+      for (const HostSub& sb : b.subs)
+        CU_OK(cudaMemcpy2DAsync(din + (size_t)sb.row * per, per * sizeof(int16_t),
+                                in + (size_t)sb.first * in_stride + (size_t)f0 * fl, in_stride * sizeof(int16_t),
+                                (size_t)nf * fl * sizeof(int16_t), sb.count, cudaMemcpyHostToDevice, d->copy_in));
       mark(d->copy_in);
       CU_OK(cudaEventRecord(ev[3 * c + 0], d->copy_in));
       CU_OK(cudaStreamWaitEvent(d->stream, ev[3 * c + 0], 0));
       mark(d->stream);
-      if (RunDevice(*d, magic, sub, din, per, dout, per, nf, d->stream) != 0) return -1;
+      if (RunDevice(*d, magic, b.hs, din, per, dout, per, nf, d->stream) != 0) return -1;
       mark(d->stream);
-      CU_OK(cudaEventRecord(d->pipe_kdone[b], d->stream));
-      CU_OK(cudaStreamWaitEvent(d->copy_out, d->pipe_kdone[b], 0));
+      CU_OK(cudaEventRecord(d->pipe_kdone[k], d->stream));
+      CU_OK(cudaStreamWaitEvent(d->copy_out, d->pipe_kdone[k], 0));
       mark(d->copy_out);
-      CU_OK(cudaMemcpy2DAsync(out + (size_t)r.first * out_stride + (size_t)f0 * fl,
-                              out_stride * sizeof(int16_t), dout, per * sizeof(int16_t),
-                              (size_t)nf * fl * sizeof(int16_t), r.count, cudaMemcpyDeviceToHost, d->copy_out));
+      for (const HostSub& sb : b.subs)
+        CU_OK(cudaMemcpy2DAsync(out + (size_t)sb.first * out_stride + (size_t)f0 * fl, out_stride * sizeof(int16_t),
+                                dout + (size_t)sb.row * per, per * sizeof(int16_t),
+                                (size_t)nf * fl * sizeof(int16_t), sb.count, cudaMemcpyDeviceToHost, d->copy_out));
       mark(d->copy_out);
-      CU_OK(cudaEventRecord(d->pipe_drained[b], d->copy_out));
-      d->pipe_used[b] = true;
+      CU_OK(cudaEventRecord(d->pipe_drained[k], d->copy_out));
+      d->pipe_used[k] = true;
     }
     d->pipe_seq += (unsigned long long)nchunks;
     if (trace) {
@@ -1110,22 +1236,23 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
   if (ticket) {
     // completion = the last copy-out of every device (the copy-out queue is in order)
     PendingBatch pb;
-    pb.ticket = g_next_ticket++;
-    for (size_t ri = 0; ri < runs.size(); ++ri) {
-      DeviceCtx* d = &g_devs[runs[ri].dev];
-      CU_OK(cudaSetDevice(runs[ri].dev));
+    for (const HostBucket& b : buckets) {
+      DeviceCtx* d = &g_devs[b.dev];
+      CU_OK(cudaSetDevice(b.dev));
       cudaEvent_t e;
       CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CU_OK(cudaEventRecord(e, d->copy_out));
-      pb.done.push_back(std::make_pair(runs[ri].dev, e));
+      pb.done.push_back(std::make_pair(b.dev, e));
     }
+    std::lock_guard<std::mutex> g(g_pend_mu);
+    pb.ticket = g_next_ticket++;
     *ticket = pb.ticket;
     g_pending.push_back(pb);
     return 0;
   }
-  for (size_t ri = 0; ri < runs.size(); ++ri) {
-    DeviceCtx* d = &g_devs[runs[ri].dev];
-    CU_OK(cudaSetDevice(runs[ri].dev));
+  for (const HostBucket& b : buckets) {
+    DeviceCtx* d = &g_devs[b.dev];
+    CU_OK(cudaSetDevice(b.dev));
     CU_OK(cudaStreamSynchronize(d->copy_out));
     CU_OK(cudaStreamSynchronize(d->stream));
   }
@@ -1133,14 +1260,19 @@ int BatchHost(void* const* hv, int n, uint32_t magic, const int16_t* in, size_t 
 }
 
 int WaitBatch(uint64_t ticket) {
-  ApiLock lk(false);
   // tickets complete in issue order per device, but callers may wait in any order
-  for (size_t i = 0; i < g_pending.size(); ++i)
-    if (g_pending[i].ticket == ticket) {
-      FinishPending(g_pending[i]);
-      g_pending.erase(g_pending.begin() + (long)i);
-      break;
-    }
+  PendingBatch mine;
+  mine.ticket = 0;
+  {
+    std::lock_guard<std::mutex> g(g_pend_mu);
+    for (size_t i = 0; i < g_pending.size(); ++i)
+      if (g_pending[i].ticket == ticket) {
+        mine = std::move(g_pending[i]);
+        g_pending.erase(g_pending.begin() + (long)i);
+        break;
+      }
+  }
+  FinishPending(mine);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return Fail(std::string("asynchronous batch failed: ") + cudaGetErrorString(e));
   return 0;
@@ -1303,7 +1435,9 @@ __global__ void interleave_kernel(const int16_t* in, T* out, int channels, int s
 // ranges: nsb_logf / nsb_sqrtf_p1 / round_s16 / fx_sqrt_floor() must equal their definitions
 // (logf, sqrtf + 1, FloatS16ToS16, spl_sqrt_floor.c:55) bit for bit; fdiv() is compared with IEEE
 // division and classified: equal, one ulp off, worse.  out[0] = hard mismatches (incl. divisions
-// more than one ulp off), out[1] = divisions one ulp off, out[2] = divisions checked.
+// more than one ulp off), out[1] = divisions one ulp off, out[2] = divisions checked, out[3] = nsb_log_rn()
+// results that are not (float)log((double)x) (both are the correctly rounded float except within ~2^-41 /
+// 2^-52 of a rounding boundary: a few per million at most), out[4] = logarithms checked.
 __device__ __forceinline__ void selftest_div(float got, float want, unsigned long long& hard,
                                              unsigned long long& ulp1, unsigned long long& ndiv) {
   ++ndiv;
@@ -1312,7 +1446,7 @@ __device__ __forceinline__ void selftest_div(float got, float want, unsigned lon
   else if (d != 0) ++hard;
 }
 __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned long long* out) {
-  unsigned long long mism = 0, ulp1 = 0, ndiv = 0;
+  unsigned long long mism = 0, ulp1 = 0, ndiv = 0, lrn = 0, nlog = 0;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint32_t h1 = pcm_mix32(seed + (uint32_t)i * 2u + (uint32_t)(i >> 31));
@@ -1341,6 +1475,16 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
       if (__float_as_uint(nsb_logf(x)) != __float_as_uint(logf(x))) ++mism;
       const float x1 = 1.f + __uint_as_float((h2 & 0x007fffffu) | (((h1 >> 9) % 30u + 97u) << 23));  // just above 1
       if (__float_as_uint(nsb_logf(x1)) != __float_as_uint(logf(x1))) ++mism;
+      // nsb_log_rn against the double-precision library logarithm rounded to float, and never more than an ulp off
+      const float xm = __uint_as_float((h2 & 0x007fffffu) | (((h1 >> 11) % 26u + 127u) << 23));   // magnitudes + 1: [1, 2^26)
+      for (int t = 0; t < 2; ++t) {
+        const float xx = t ? x1 : xm;
+        const float got = nsb_log_rn(xx), want = (float)log((double)xx);
+        const int d = __float_as_int(got) - __float_as_int(want);
+        ++nlog;
+        if (d != 0) ++lrn;
+        if (d > 1 || d < -1) ++mism;
+      }
     }
     {
       // nsb_sqrtf_p1 == sqrtf + 1 on [0, 2^70): squared spectral magnitudes incl. the tiny end
@@ -1364,6 +1508,8 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
   if (mism) atomicAdd(out, mism);
   if (ulp1) atomicAdd(out + 1, ulp1);
   atomicAdd(out + 2, ndiv);
+  if (lrn) atomicAdd(out + 3, lrn);
+  atomicAdd(out + 4, nlog);
 }
 
 template <typename T>
@@ -1790,7 +1936,7 @@ int WebRtcNsB200_SetCreateDevice(int device) {
     if (EnsureDevices() != 0) return -1;
     if (device >= (int)g_devs.size()) return Fail("bad device index");
   }
-  g_create_device = device;
+  t_create_device = device;
   return 0;
 }
 int WebRtcNsB200_DeviceCount(void) {
@@ -1818,21 +1964,23 @@ int WebRtcNsB200_SelfTestStats(uint64_t n_cases, uint64_t* stats) {
   DeviceCtx* d;
   if (DeviceReady(dev, &d) != 0) return -1;
   unsigned long long* bad = nullptr;
-  CU_OK(cudaMalloc(&bad, 3 * sizeof(*bad)));
-  CU_OK(cudaMemsetAsync(bad, 0, 3 * sizeof(*bad), d->stream));
+  CU_OK(cudaMalloc(&bad, 5 * sizeof(*bad)));
+  CU_OK(cudaMemsetAsync(bad, 0, 5 * sizeof(*bad), d->stream));
   selftest_kernel<<<148 * 4, 256, 0, d->stream>>>(n_cases, 12345u, bad);
   ++g_launches;
-  unsigned long long h[3] = {0, 0, 0};
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
   CU_OK(cudaMemcpyAsync(h, bad, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
   CU_OK(cudaStreamSynchronize(d->stream));
   cudaFree(bad);
-  for (int i = 0; i < 3; ++i) stats[i] = h[i];
+  for (int i = 0; i < 5; ++i) stats[i] = h[i];
   return 0;
 }
 int WebRtcNsB200_SelfTest(uint64_t n_cases) {
-  uint64_t st[3] = {0, 0, 0};
+  uint64_t st[5] = {0, 0, 0, 0, 0};
   if (WebRtcNsB200_SelfTestStats(n_cases, st) != 0) return -1;
   if (st[0] != 0) return Fail("self-test: " + std::to_string(st[0]) + " arithmetic mismatches");
+  if (st[3] * 100000ull > st[4])
+    return Fail("self-test: " + std::to_string(st[3]) + " of " + std::to_string(st[4]) + " logarithms not the rounded double-precision one");
   // fdiv(): correctly rounded except for a handful of near-halfway quotients (ns_warp.cuh)
   if (st[1] * 1000000ull > st[2] * 2ull)
     return Fail("self-test: " + std::to_string(st[1]) + " of " + std::to_string(st[2]) + " divisions one ulp off");

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <vector_functions.h>
 
 #include "nsf_layout.h"
 
@@ -28,6 +29,98 @@ inline void nsf_make_window(int ana, float* w) {
     else v = sin(kPi * (ana - i) / (2.0 * rise));
     w[i] = (float)(floor(v * 1e8 + 0.5) / 1e8);
   }
+}
+
+// ---- tables of the forward FFT, which reproduces the rounding order of the reference's Ooura rdft
+// (ns_warp.cuh ooura_fwd; utility/fft4g.c).  Everything below is evaluated in the reference's own
+// precision and order -- angles formed in float, cos/sin in double rounded to float, the third
+// twiddle of a group derived from the other two in float -- because the kernel must multiply by the
+// very same floats (checked against WebRtc_rdft through the emulator in tests/test_emulated_kernels.py
+// and on the device in tests/test_gpu_float_parity.py).
+inline unsigned nsf_bit_reverse(unsigned v, int bits) {
+  unsigned r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1u) << (bits - 1 - b);
+  return r;
+}
+// Quarter-circle twiddles W[q] = (cos, sin)(pi q / (n/4)), q < n/8, in bit-reversed order (makewt, fft4g.c:642).
+inline void nsf_ooura_quarter(int n, float2* W) {
+  const int nw = n >> 2, nwh = nw >> 1, nq = nw >> 1;
+  int qbits = 0;
+  while ((1 << qbits) < nq) ++qbits;
+  const float delta = (float)atan(1.0) / (float)nwh;
+  float w[64];
+  w[0] = 1.f;
+  w[1] = 0.f;
+  w[nwh] = (float)cos((double)(delta * (float)nwh));
+  w[nwh + 1] = w[nwh];
+  for (int j = 2; j < nwh; j += 2) {
+    const float ang = delta * (float)j;
+    const float x = (float)cos((double)ang), y = (float)sin((double)ang);
+    w[j] = x;
+    w[j + 1] = y;
+    w[nw - j] = y;
+    w[nw - j + 1] = x;
+  }
+  for (int q = 0; q < nq; ++q) {
+    const unsigned r = nsf_bit_reverse((unsigned)q, qbits);
+    W[q] = make_float2(w[2 * r], w[2 * r + 1]);
+  }
+}
+// The three output twiddles of butterfly group g of any radix-4 pass (cft1st / cftmdl, fft4g.c:1002,1107).
+// Group 1 is the pi/4 group, evaluated by the reference as c * (a -+ b): stored as (c, 0), i, (-c, 0) for the
+// kernel's `diag` form.  volatile: the float products must round exactly once, whatever the host compiler does.
+inline void nsf_ooura_group(const float2* W, int g, float2* w1, float2* w2, float2* w3) {
+  *w1 = *w2 = *w3 = make_float2(1.f, 0.f);
+  if (g == 0) return;
+  const int p = g >> 1;
+  const float ar = W[p].x, ai = W[p].y;
+  const bool odd = (g & 1) != 0;
+  *w1 = odd ? W[2 * p + 1] : W[2 * p];
+  *w2 = odd ? make_float2(-ai, ar) : make_float2(ar, ai);
+  const float h = odd ? ar : ai;
+  volatile float t = 2.f * h;
+  volatile float u = t * w1->y;
+  volatile float r3 = w1->x - u;
+  u = t * w1->x;
+  volatile float i3 = u - w1->y;
+  *w3 = make_float2(r3, i3);
+  if (g == 1) {
+    *w1 = make_float2(w1->x, 0.f);
+    *w3 = make_float2(-w1->x, 0.f);
+  }
+}
+// img_split: 129 float2 (real-input split per bin, rftfsub fft4g.c:1234 + :352-354); img_otw: kOouraTwF2 float2.
+inline void nsf_fill_ooura(int ana, float2* img_split, float2* img_otw) {
+  const int nc = ana / 2, ncq = ana >> 2, nch = ncq >> 1;
+  float2 W[32];
+  nsf_ooura_quarter(ana, W);
+  // half-cosine table of makect (fft4g.c:671)
+  float c[65];
+  {
+    const float delta = (float)atan(1.0) / (float)nch;
+    c[0] = (float)cos((double)(delta * (float)nch));
+    c[nch] = 0.5f * c[0];
+    for (int j = 1; j < nch; ++j) {
+      const float ang = delta * (float)j;
+      c[j] = 0.5f * (float)cos((double)ang);
+      c[ncq - j] = 0.5f * (float)sin((double)ang);
+    }
+  }
+  for (int k = 0; k <= nc; ++k) {
+    float2 w = make_float2(0.f, 0.f);            // bin nc/2 passes through
+    if (k == 0) w = make_float2(0.f, 0.5f);       // a[0] + a[1]
+    else if (k == nc) w = make_float2(0.f, -0.5f);  // a[0] - a[1]
+    else if (k < nc / 2) w = make_float2(0.5f - c[ncq - k], c[k]);
+    else if (k > nc / 2) w = make_float2(0.5f - c[ncq - (nc - k)], -c[nc - k]);
+    img_split[k] = w;
+  }
+  // pass 1: lane H owns group rev(H); pass 2: index l owns group rev(l)
+  const int lanes = nc / 4, lbits = lanes == 32 ? 5 : 4, gbits = lanes == 32 ? 3 : 2;
+  for (int H = 0; H < lanes; ++H)
+    nsf_ooura_group(W, (int)nsf_bit_reverse((unsigned)H, lbits), &img_otw[H], &img_otw[32 + H], &img_otw[64 + H]);
+  for (int l = 0; l < (1 << gbits); ++l)
+    nsf_ooura_group(W, (int)nsf_bit_reverse((unsigned)l, gbits), &img_otw[96 + l], &img_otw[96 + 8 + l], &img_otw[96 + 16 + l]);
+  img_otw[120] = make_float2(W[1].x, -W[1].x);   // pass 3, group 1: c = cos(pi/4) as the reference rounds it
 }
 
 template <typename Tables>
@@ -73,6 +166,7 @@ inline void nsf_fill_tables(Tables* t) {
     float2* tw12 = reinterpret_cast<float2*>(img + kNsfImgTw12);
     for (int i = 0; i < 96; ++i) tw12[i] = t->tw[((i & 31) * (i / 32 + 1) * (256 / nc)) & 255];
     for (int i = 0; i < 24; ++i) tw12[96 + i] = t->tw[(((i & 7) % m) * (i / 8 + 1) * (256 / l)) & 255];
+    nsf_fill_ooura(ana, reinterpret_cast<float2*>(img + kNsfImgSplit), reinterpret_cast<float2*>(img + kNsfImgOtw));
   }
 }
 

@@ -30,30 +30,32 @@
 
 namespace nsb200 {
 
-// 2-warp CTAs, 8 per SM (128 registers, no spills): 16 resident streams per SM -- the best of
-// 7/8/9/10 CTAs per SM and of 1/2/4/8 warps per CTA on the B200 (profiles/README.md).
+// 4-warp CTAs, 4 per SM (128 registers, no spills): 16 resident streams per SM -- the best of 14/16/18/20
+// warps per SM; 1/2/4/8 warps per CTA run alike (profiles/README.md), and four share one copy of the
+// 6.6 KB table block, which pays for the staging arrays of the sequential sums.
 #ifndef NSF_WARPS_PER_CTA
-#define NSF_WARPS_PER_CTA 2
+#define NSF_WARPS_PER_CTA 4
 #endif
 #ifndef NSF_FRAME_SYNC
 #define NSF_FRAME_SYNC 0
 #endif
 constexpr int kNsfWarpsPerCta = NSF_WARPS_PER_CTA;
 #ifndef NSF_CTAS_PER_SM
-#define NSF_CTAS_PER_SM 8
+#define NSF_CTAS_PER_SM 4
 #endif
 constexpr int kNsfCtasPerSm = NSF_CTAS_PER_SM;
 // Per-CTA shared memory: the table image (nsf_layout.h: win 256 | tw 512 | logi 132 | pad | regrouped
 // twiddles 240) followed by the mbarriers of the TMA bulk copies: one for the tables, two per warp
 // (header + sample histories | per-bin records).
-static_assert(kNsfImgTw12 + 2 * kFftTw12F2 == kNsfTableImgWords, "table image layout");
+static_assert(kNsfImgTw12 + 2 * kFftTw12F2 == kNsfImgSplit && kNsfImgOtw + 2 * kOouraTwF2 <= kNsfTableImgWords, "table image layout");
 constexpr int kNsfCtaBarWords = (2 * (1 + 2 * kNsfWarpsPerCta) + 3) / 4 * 4;
 constexpr int kNsfCtaTableWords = kNsfTableImgWords + kNsfCtaBarWords;
 // Per-warp shared memory (32-bit words): header x2 | bin records | FFT scratch | analysis block
 // (256) | synthesis overlap (96) | split: aux arrays + Process block (256) | high-band delay blocks.
 // The sample histories live in shared memory, not registers: the register budget of the per-bin
 // phases decides how far ptxas can interleave their dependent division chains.
-constexpr int kNsfWarpWordsBase = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2 + 256 + 96;
+constexpr int kNsfStageWords = 4 * 132;   // four staging arrays of the sequential sums (chain_sum4)
+constexpr int kNsfWarpWordsBase = 2 * kNsfHdrWords + 129 * kNsfBinRec + 2 * kFftScratchF2 + 256 + 96 + kNsfStageWords;
 template <bool SPLIT, int NB>
 struct NsfWarpWords {
   static constexpr int value = kNsfWarpWordsBase + (SPLIT ? 4 * kNsfAuxStride + 256 : 0) + (NB - 1) * 256;
@@ -70,6 +72,7 @@ struct NsfGeo {
   static constexpr int kFP = kFrame / 2;        // frame sample pairs (80 / 40)
   static constexpr int kHP = (ANA - kFrame) / 2;  // history pairs (48 / 24)
   static constexpr int kTP = ANA / 2;           // all pairs
+  static constexpr int kStg = ANA == 256 ? 132 : 68;   // words per staging array of chain_sum4: >= kBins, = 4 (mod 32)
 };
 
 NSB_DEV int pad_idx(int k) { return k + ((k >> 6) << 1); }
@@ -140,18 +143,22 @@ NSB_DEV void nsf_extract_params(float* H, int* hist, int lane) {
   int* hLrt = hist;
   int* hFlat = hist + 1000;
   int* hDiff = hist + 2000;
-  // LRT fluctuation.
+  // LRT fluctuation (ns_core.c:340-358).  The reference adds the bins' terms in turn in single precision, and
+  // `fluct < 0.05` below switches a feature on or off: every lane walks all 1000 bins in that order (once per
+  // 500 frames), the counters fetched 32 at a time and handed round by shuffle.
   float avg = 0.f, avgC = 0.f, avgSq = 0.f;
   int num = 0;
-  for (int i = lane; i < 1000; i += 32) {
-    const int c = __ldcg(hLrt + i);  // counters are bumped by L2 atomics: bypass L1
-    const float mid = ((float)i + 0.5f) * 0.1f;
-    if (mid <= 1.f) { avg += c * mid; num += c; }
-    avgSq += c * mid * mid;
-    avgC += c * mid;
+  for (int base = 0; base < 1000; base += 32) {
+    const int mine = base + lane < 1000 ? __ldcg(hLrt + base + lane) : 0;  // counters are bumped by L2 atomics: bypass L1
+    const int nl = 1000 - base < 32 ? 1000 - base : 32;
+    for (int l = 0; l < nl; ++l) {
+      const int c = __shfl_sync(kFullMask, mine, l);
+      const float mid = ((float)(base + l) + 0.5f) * 0.1f;
+      if (mid <= 1.f) { avg += c * mid; num += c; }
+      avgSq += c * mid * mid;
+      avgC += c * mid;
+    }
   }
-  warp_sum3(avg, avgC, avgSq);
-  num = warp_sum_i(num);
   if (num > 0) avg = avg / (float)num;
   avgC = avgC / 500.f;
   avgSq = avgSq / 500.f;
@@ -225,6 +232,8 @@ nsf_process_kernel(const NsfLaunch p) {
   float2* s_tw = reinterpret_cast<float2*>(smem + kNsfImgTw);
   float* s_logi = smem + kNsfImgLogi;
   float2* s_tw12 = reinterpret_cast<float2*>(smem + kNsfImgTw12);
+  const float2* s_split = reinterpret_cast<const float2*>(smem + kNsfImgSplit);   // real-input split of the forward FFT
+  const float2* s_otw = reinterpret_cast<const float2*>(smem + kNsfImgOtw);       // its twiddles per (pass, lane)
   mbar_t* bars = reinterpret_cast<mbar_t*>(smem + kNsfTableImgWords);
 
   const int lane = lane_id();
@@ -247,12 +256,13 @@ nsf_process_kernel(const NsfLaunch p) {
   float2* scr = reinterpret_cast<float2*>(B + 129 * kNsfBinRec);  // FFT scratch (8-byte aligned)
   float2* blkA = scr + kFftScratchF2;          // analysis block [history | frame], 128 pairs (analyzeBuf)
   float2* ovl = blkA + 128;                    // synthesis overlap, 48 pairs (head of syntBuf)
-  float* X_noise = reinterpret_cast<float*>(ovl + 48);              // split mode: self->noise
+  float* stg = reinterpret_cast<float*>(ovl + 48);                  // staging arrays of the sequential sums (16-byte aligned)
+  float* X_noise = stg + kNsfStageWords;                            // split mode: self->noise
   float* X_prob = X_noise + kNsfAuxStride;                          //   self->speechProb
   float* X_param = X_prob + kNsfAuxStride;                          //   self->parametricNoise
   float* X_magnP = X_param + kNsfAuxStride;                         //   self->magnPrevProcess
   float2* blkP = reinterpret_cast<float2*>(X_magnP + kNsfAuxStride);  // split mode: Process block (dataBuf)
-  float2* blkH = reinterpret_cast<float2*>(reinterpret_cast<float*>(ovl + 48) + (SPLIT ? 4 * kNsfAuxStride + 256 : 0));  // high-band delay blocks (dataBufHB)
+  float2* blkH = reinterpret_cast<float2*>(stg + kNsfStageWords + (SPLIT ? 4 * kNsfAuxStride + 256 : 0));  // high-band delay blocks (dataBufHB)
 
   // ---- tables and state: HBM -> shared by TMA bulk copies.  Everything a stream needs is in
   // flight after a handful of instructions of one lane and one dependent load (the slot), where
@@ -292,6 +302,8 @@ nsf_process_kernel(const NsfLaunch p) {
     if (SPLIT) bulk_load(X_noise, gS + kNsfOffAux, 4 * kNsfAuxStride * 4, barB);
   }
   bool state_ready = false;
+  // the staging arrays' tails beyond the last bin stay +0.f for the whole launch (chain_sum4 adds them)
+  if (lane < 4 * (G::kStg - G::kBins)) stg[(lane / (G::kStg - G::kBins)) * G::kStg + G::kBins + lane % (G::kStg - G::kBins)] = 0.f;
   // Prefetch across CTAs: the stream that the block scheduler will start in this warp's place about
   // one wave from now (batch entry sidx + resident warps) gets its state and first frame pulled
   // into L2, so that its own bulk copies find them there instead of in DRAM.  One wave of state is
@@ -465,15 +477,19 @@ nsf_process_kernel(const NsfLaunch p) {
 
       // ---- (c) forward FFT (ns_core.c:886-911)
       if (!SPLIT) energy1 = warp_sum(energy1);
-      warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
+      ooura_fwd<G::kNC>(v, scr, s_otw, lane);
       if (lane < G::kL) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
+        for (int q = 0; q < 4; ++q) scr[pad_idx(ooura_out_index<G::kNC>(lane, q))] = v[q];
       }
       __syncwarp();
 
+      if (!state_ready) {   // the per-bin records: first frame of a launch only
+        mbar_wait_warp(barB, 0);
+        state_ready = true;
+      }
       float lmagn[G::kSlots];
-      float sigE = 0.f, sumMagn = 0.f;
+      float smoothPrev[G::kSlots], magnPrevA[G::kSlots];
       {
         float re[G::kSlots], im[G::kSlots];
 #pragma unroll
@@ -482,19 +498,28 @@ nsf_process_kernel(const NsfLaunch p) {
           const int k = nyq ? G::kNC : lane + 32 * j;
           const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
           const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
-          const float2 w = s_tw[k * (256 / ANA)];
-          // E + O * w with E = (zk + conj(zm)) / 2, O = -i (zk - conj(zm)) / 2.  The halves are taken once
-          // at the end: scaling by a power of two commutes with every rounding, so these are the bits of
-          // er + (orr * w.x - oi * w.y) with er, orr, oi halved first, in 12 operations instead of 14.
-          const float ea = zk.x + zm.x, eb = zk.y - zm.y, os = zk.y + zm.y, od = zk.x - zm.x;
-          re[j] = 0.5f * (ea + (os * w.x + od * w.y));
-          im[j] = 0.5f * (eb + (os * w.y - od * w.x));
+          // the reference's real-input split (fft4g.c:1234-1256 and :352-354) seen from bin k: with
+          // (wr, wi) = s_split[k] -- wi negated on the mirror side, (0, +-1/2) at bins 0 and N/2 so that
+          // the same expression yields a[0] +- a[1] -- the same additions and products, rounding for rounding
+          const float2 w = s_split[k];
+          const float xd = zk.x - zm.x, xs = zk.y + zm.y;
+          re[j] = zk.x - (w.x * xd - w.y * xs);
+          im[j] = zk.y - (w.x * xs + w.y * xd);
           if (nyq || k == 0) im[j] = 0.f;
-          magn[j] = nsb_sqrtf_p1(re[j] * re[j] + im[j] * im[j]);
-          lmagn[j] = nsb_logf(magn[j]);
+          const float e = re[j] * re[j] + im[j] * im[j];
+          magn[j] = nsb_sqrtf_p1(e);
+          lmagn[j] = nsb_log_rn(magn[j]);   // (float)log((double)magn): ns_core.c:228
+          const float4 r2 = *reinterpret_cast<const float4*>(B + k * kNsfBinRec + 8);  // noisePrev magnPrev logLrt pause
+          noisePrev[j] = r2.x;
+          magnPrevA[j] = r2.y;
+          logLrt[j] = r2.z;
+          mpause[j] = r2.w;
+          // terms of the four sums of pass A (below), bin by bin
           if (!nyq || lane == 0) {
-            sigE += re[j] * re[j] + im[j] * im[j];
-            sumMagn += magn[j];
+            stg[k] = e;                                   // signalEnergy   ns_core.c:1090
+            stg[G::kStg + k] = magn[j];                   // sumMagn        :1091
+            stg[2 * G::kStg + k] = k == 0 ? 0.f : lmagn[j];   // flatness numerator, bins >= 1   :540-542
+            stg[3 * G::kStg + k] = r2.w;                  // avgPause       :609
           }
         }
         __syncwarp();  // every lane has read its mirrored points: scratch is free again
@@ -506,12 +531,17 @@ nsf_process_kernel(const NsfLaunch p) {
           }
         }
       }
-      if (!state_ready) {
-        mbar_wait_warp(barB, 0);
-        state_ready = true;
+      // ---- pass A: signalEnergy, sumMagn, sum of lmagn, sum of magnAvgPause, each summed bin after bin as the
+      // reference sums them (chain_sum4: four lanes, one chain each).  A 129-step dependent chain; it sits in
+      // one basic block with the tracker updates of (d), which need none of its results.
+      float sigE, sumMagn, sumLog, sumPause;
+      {
+        const float c = chain_sum4<G::kStg, G::kStg>(stg, lane);
+        sigE = __shfl_sync(kFullMask, c, 0);
+        sumMagn = __shfl_sync(kFullMask, c, 1);
+        sumLog = __shfl_sync(kFullMask, c, 2);
+        sumPause = __shfl_sync(kFullMask, c, 3);
       }
-      // (after the wait: in one basic block with the tracker updates below, which hide its latency)
-      warp_sum2(sigE, sumMagn);
       const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
 
       // ---- (d) NoiseEstimation (ns_core.c:217-285)
@@ -533,7 +563,6 @@ nsf_process_kernel(const NsfLaunch p) {
         rc1[s] = frcp_nr(c1[s]);
         cf[s] = (float)cnt[s];
       }
-      float smoothPrev[G::kSlots];
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
@@ -570,7 +599,7 @@ nsf_process_kernel(const NsfLaunch p) {
         for (int j = 0; j < G::kSlots; ++j) {
           const bool nyq = (j == G::kSlots - 1);
           float* R = B + (nyq ? G::kNC : lane + 32 * j) * kNsfBinRec;
-          const float q = expf(R[sel]);
+          const float q = nsb_exp_rn(R[sel]);   // (float)exp(lquantile): ns_core.c:266,277
           noise[j] = q;
           if (!nyq || lane == 0) R[kB_quantile] = q;
         }
@@ -578,17 +607,22 @@ nsf_process_kernel(const NsfLaunch p) {
 
       // ---- (e) start-up: white / pink parametric noise (ns_core.c:1088-1162)
       if (blockInd < 50) {
+        // The least-squares fit below subtracts nearly equal products of these sums: summed in any other
+        // order than the reference's (bins 5, 6, ... in turn, ns_core.c:1088-1100) its result moves by 1e-5
+        // relative -- by far the largest non-branching deviation the kernel could have (oracle experiment,
+        // profiles/r2_float_parity.md).  Fifty frames per stream: every lane runs the sequential sums.
         float slm = 0.f, slilm = 0.f;
 #pragma unroll
-        for (int j = 0; j < G::kSlots; ++j) {
-          const bool nyq = (j == G::kSlots - 1);
-          const int k = nyq ? G::kNC : lane + 32 * j;
-          if (k >= 5 && (!nyq || lane == 0)) {
-            slm += lmagn[j];
-            slilm += s_logi[k] * lmagn[j];
+        for (int j = 0; j < G::kSlots - 1; ++j) {
+#pragma unroll 1
+          for (int l = (j == 0 ? 5 : 0); l < 32; ++l) {
+            const float lm = __shfl_sync(kFullMask, lmagn[j], l);
+            slm += lm;
+            slilm += s_logi[l + 32 * j] * lm;
           }
         }
-        warp_sum2(slm, slilm);
+        slm += lmagn[G::kSlots - 1];   // bin N/2 sits in every lane
+        slilm += s_logi[G::kNC] * lmagn[G::kSlots - 1];
         const float sli = T->sum_log_i[ANA == 256 ? 0 : 1];
         const float slisq = T->sum_log_i_sq[ANA == 256 ? 0 : 1];
         float white = Hr[kH_white] + sumMagn / magnLenF * overdrive;
@@ -609,7 +643,7 @@ nsf_process_kernel(const NsfLaunch p) {
         Hw[kH_pinkExp] = pinkExp;
         float pnum = 0.f, pexp = 0.f;
         if (pinkExp > 0.f) {
-          pnum = expf(pinkNum / (float)(blockInd + 1));
+          pnum = nsb_exp_rn(pinkNum / (float)(blockInd + 1));
           pnum *= (float)(blockInd + 1);
           pexp = pinkExp / (float)(blockInd + 1);
         }
@@ -627,7 +661,7 @@ nsf_process_kernel(const NsfLaunch p) {
             int kub = k < 5 ? 5 : k;
             asm volatile("" : "+r"(kub));
             const float ub = (float)kub;
-            parametric[j] = pnum / powf(ub, pexp);
+            parametric[j] = nsb_div_pow_rn(pnum, ub, pexp);   // (float)(parametric_num / pow(use_band, parametric_exp))
           }
           noise[j] *= (float)blockInd;
           const float t = parametric[j] * (float)(50 - blockInd);
@@ -644,42 +678,43 @@ nsf_process_kernel(const NsfLaunch p) {
         Hw[kH_feat + 5] = feat5;
       }
 
-      // ---- (g) ComputeSnr (ns_core.c:566-588) + feature sums
+      // ---- (g) ComputeSnr (ns_core.c:566-588) and the first loop of SpeechNoiseProb (:660-679): neither needs
+      // anything from FeatureUpdate, and the sum over the updated logLrtTimeAvg rides in pass B
       float snrPrior[G::kSlots], snrPost[G::kSlots];
-      float sumPause = 0.f, sumLog = 0.f;
+      const float avgPause = NSB_FDIV_C(sumPause, kMagnLenF);
+      const float avgMagn = NSB_FDIV_C(sumMagn, kMagnLenF);
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
         const int k = nyq ? G::kNC : lane + 32 * j;
-        const float* R = B + k * kNsfBinRec;
-        const float smooth = smoothPrev[j];
-        const float4 r2 = *reinterpret_cast<const float4*>(R + 8);  // noisePrev magnPrev logLrt pause
-        noisePrev[j] = r2.x;
-        logLrt[j] = r2.z;
-        mpause[j] = r2.w;
-        prevEst[j] = fdiv(r2.y, r2.x + 0.0001f) * smooth;
+        prevEst[j] = fdiv(magnPrevA[j], noisePrev[j] + 0.0001f) * smoothPrev[j];
         // branch-free: a branch per slot would fence the five division chains off from each other
         const float post = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
         snrPost[j] = magn[j] > noise[j] ? post : 0.f;
         snrPrior[j] = 0.98f * prevEst[j] + (1.f - 0.98f) * snrPost[j];
-        if (!nyq || lane == 0) {
-          sumPause += mpause[j];
-          if (k >= 1) sumLog += lmagn[j];
-        }
-      }
-      // first loop of (i) SpeechNoiseProb (ns_core.c:660-679) here: it needs nothing from (h), and its
-      // sum shares one reduction with the two above instead of paying a reduction latency of its own
-      float lsum = 0.f;
-#pragma unroll
-      for (int j = 0; j < G::kSlots; ++j) {
-        const bool nyq = (j == G::kSlots - 1);
         const float t1 = 1.f + 2.f * snrPrior[j];
         const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
         const float bessel = (snrPost[j] + 1.f) * t2;
-        logLrt[j] += 0.5f * (bessel - nsb_logf(t1) - logLrt[j]);
-        if (!nyq || lane == 0) lsum += logLrt[j];
+        logLrt[j] += 0.5f * (bessel - nsb_log_rn(t1) - logLrt[j]);
+        // terms of the four sums of pass B (ComputeSpectralDifference :620-626, SpeechNoiseProb :678)
+        const float dm = magn[j] - avgMagn, dp = mpause[j] - avgPause;
+        if (!nyq || lane == 0) {
+          stg[k] = dm * dp;
+          stg[G::kStg + k] = dp * dp;
+          stg[2 * G::kStg + k] = dm * dm;
+          stg[3 * G::kStg + k] = logLrt[j];
+        }
       }
-      warp_sum3(sumPause, sumLog, lsum);
+      __syncwarp();
+      // ---- pass B: covMagnPause, varPause, varMagn, sum of logLrtTimeAvg, bin after bin
+      float cov, varP, varM, lsum;
+      {
+        const float c = chain_sum4<G::kStg, G::kStg>(stg, lane);
+        cov = __shfl_sync(kFullMask, c, 0);
+        varP = __shfl_sync(kFullMask, c, 1);
+        varM = __shfl_sync(kFullMask, c, 2);
+        lsum = __shfl_sync(kFullMask, c, 3);
+      }
 
       // ---- (h) FeatureUpdate (ns_core.c:755-791)
       float feat0, feat4;
@@ -688,25 +723,11 @@ nsf_process_kernel(const NsfLaunch p) {
         float den = sumMagn - __shfl_sync(kFullMask, magn[0], 0);
         den = NSB_FDIV_C(den, kMagnLenF);
         const float num = NSB_FDIV_C(sumLog, kMagnLenF);
-        const float sf = fdiv(expf(num), den);
+        const float sf = fdiv(nsb_exp_rn(num), den);
         feat0 = Hr[kH_feat + 0];
         feat0 += 0.3f * (sf - feat0);
         Hw[kH_feat + 0] = feat0;
         // spectral difference (:595-634)
-        const float avgPause = NSB_FDIV_C(sumPause, kMagnLenF);
-        const float avgMagn = NSB_FDIV_C(sumMagn, kMagnLenF);
-        float cov = 0.f, varP = 0.f, varM = 0.f;
-#pragma unroll
-        for (int j = 0; j < G::kSlots; ++j) {
-          const bool nyq = (j == G::kSlots - 1);
-          if (!nyq || lane == 0) {
-            const float dm = magn[j] - avgMagn, dp = mpause[j] - avgPause;
-            cov += dm * dp;
-            varP += dp * dp;
-            varM += dm * dm;
-          }
-        }
-        warp_sum3(cov, varP, varM);
         cov = NSB_FDIV_C(cov, kMagnLenF);
         varP = NSB_FDIV_C(varP, kMagnLenF);
         varM = NSB_FDIV_C(varM, kMagnLenF);
@@ -754,16 +775,21 @@ nsf_process_kernel(const NsfLaunch p) {
         // priorModelPars may have been re-estimated a few lines up (synced): read Hw
         const float thr0 = Hw[kH_priorPars + 0], thr1 = Hw[kH_priorPars + 1], thr2 = Hw[kH_priorPars + 3];
         const int sgn = (int)Hw[kH_priorPars + 2];
+        // the three sigmoid maps take (float)tanh((double)x): one evaluation, lanes 0-2 an argument each
         float width = lrtAvg < thr0 ? 8.f : 4.f;
-        const float ind0 = 0.5f * (tanhf(width * (lrtAvg - thr0)) + 1.f);
+        const float a0 = width * (lrtAvg - thr0);
         const float sfv = feat0;
         width = 4.f;
         if (sgn == 1 && sfv > thr1) width = 8.f;
         if (sgn == -1 && sfv < thr1) width = 8.f;
-        const float ind1 = 0.5f * (tanhf((float)sgn * width * (thr1 - sfv)) + 1.f);
+        const float a1 = (float)sgn * width * (thr1 - sfv);
         const float sdv = feat4;
         width = sdv < thr2 ? 8.f : 4.f;
-        const float ind2 = 0.5f * (tanhf(width * (sdv - thr2)) + 1.f);
+        const float a2 = width * (sdv - thr2);
+        const float th = nsb_tanh_rn(lane == 0 ? a0 : (lane == 1 ? a1 : a2));
+        const float ind0 = 0.5f * (__shfl_sync(kFullMask, th, 0) + 1.f);
+        const float ind1 = 0.5f * (__shfl_sync(kFullMask, th, 1) + 1.f);
+        const float ind2 = 0.5f * (__shfl_sync(kFullMask, th, 2) + 1.f);
         const float indPrior = Hw[kH_priorPars + 4] * ind0 + Hw[kH_priorPars + 5] * ind1 +
                                Hw[kH_priorPars + 6] * ind2;
         prior = Hr[kH_priorSpeechProb];
@@ -774,7 +800,7 @@ nsf_process_kernel(const NsfLaunch p) {
         const float gainPrior = fdiv(1.f - prior, prior + 0.0001f);
 #pragma unroll
         for (int j = 0; j < G::kSlots; ++j) {
-          float inv = expf(-logLrt[j]);
+          float inv = nsb_exp_rn(-logLrt[j]);   // (float)exp(-logLrtTimeAvg[i]): ns_core.c:744
           inv = gainPrior * inv;
           prob[j] = fdiv(1.f, 1.f + inv);
         }
@@ -858,10 +884,10 @@ nsf_process_kernel(const NsfLaunch p) {
       energy1 = warp_sum(energy1);
       nzP = energy1 != 0.f;
       if (nzP) {
-        warp_fft<G::kNC, +1>(v, scr, s_tw, s_tw12, lane);
+        ooura_fwd<G::kNC>(v, scr, s_otw, lane);
         if (lane < G::kL) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) scr[pad_idx(fft_out_index<G::kNC>(lane, q))] = v[q];
+          for (int q = 0; q < 4; ++q) scr[pad_idx(ooura_out_index<G::kNC>(lane, q))] = v[q];
         }
         __syncwarp();
         float re[G::kSlots], im[G::kSlots];
@@ -871,13 +897,13 @@ nsf_process_kernel(const NsfLaunch p) {
           const int k = nyq ? G::kNC : lane + 32 * j;
           const float2 zk = scr[pad_idx(k & (G::kNC - 1))];
           const float2 zm = scr[pad_idx((G::kNC - k) & (G::kNC - 1))];
-          const float2 w = s_tw[k * (256 / ANA)];
-          // E + O * w with E = (zk + conj(zm)) / 2, O = -i (zk - conj(zm)) / 2.  The halves are taken once
-          // at the end: scaling by a power of two commutes with every rounding, so these are the bits of
-          // er + (orr * w.x - oi * w.y) with er, orr, oi halved first, in 12 operations instead of 14.
-          const float ea = zk.x + zm.x, eb = zk.y - zm.y, os = zk.y + zm.y, od = zk.x - zm.x;
-          re[j] = 0.5f * (ea + (os * w.x + od * w.y));
-          im[j] = 0.5f * (eb + (os * w.y - od * w.x));
+          // the reference's real-input split (fft4g.c:1234-1256 and :352-354) seen from bin k: with
+          // (wr, wi) = s_split[k] -- wi negated on the mirror side, (0, +-1/2) at bins 0 and N/2 so that
+          // the same expression yields a[0] +- a[1] -- the same additions and products, rounding for rounding
+          const float2 w = s_split[k];
+          const float xd = zk.x - zm.x, xs = zk.y + zm.y;
+          re[j] = zk.x - (w.x * xd - w.y * xs);
+          im[j] = zk.y - (w.x * xs + w.y * xd);
           if (nyq || k == 0) im[j] = 0.f;
           magn[j] = nsb_sqrtf_p1(re[j] * re[j] + im[j] * im[j]);
           const float* R = B + k * kNsfBinRec;

@@ -56,10 +56,14 @@ enum : int {
 
 // Read-only per-device tables.  img[v] (v = 0: 256-point analysis, 1: 128-point) is the image of
 // the kernel's per-CTA table block exactly as it sits in shared memory -- window | twiddles |
-// log(i) | pad | twiddles of FFT passes 1-2 regrouped per (factor, lane) (ns_warp.cuh
-// fft_fill_tw12) -- so that a CTA fetches it with one TMA bulk copy.
+// log(i) | pad | twiddles of the inverse FFT's passes 1-2 regrouped per (factor, lane) (ns_warp.cuh
+// fft_fill_tw12) | real-input split and twiddles of the forward FFT, which follows the reference's
+// rounding order (ns_warp.cuh ooura_fwd) -- so that a CTA fetches it with one TMA bulk copy.
 enum : int {
-  kNsfImgWin = 0, kNsfImgTw = 256, kNsfImgLogi = 768, kNsfImgTw12 = 912, kNsfTableImgWords = 1152,
+  kNsfImgWin = 0, kNsfImgTw = 256, kNsfImgLogi = 768, kNsfImgTw12 = 912,
+  kNsfImgSplit = 1152,   // 129 float2: real-input split of the forward FFT per bin (nsf_host_init.h)
+  kNsfImgOtw = 1412,     // 122 float2: forward-FFT twiddles per (pass, lane) (ns_warp.cuh ooura_fwd)
+  kNsfTableImgWords = 1656,
 };
 struct NsfTables {
   alignas(16) float img[2][kNsfTableImgWords];

@@ -13,7 +13,8 @@ call walking F = --frames-per-step 10-ms frames of every stream; with the defaul
             kernel is issue-bound (roofline.issue), so the HBM fraction is small by construction
   roofline_tick  the same kernel at F = 1 over --tick-streams streams (the API-faithful 10 ms tick, every
             launch moves the whole per-stream state): the regime the HBM roofline bounds
-  cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref) on the host cores
+  cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref) on the host cores, driven like the
+            GPU arm (persistent handles, same warm-up, same frames of every stream; never loads the product .so)
 
 N > 1: one process per GPU under torchrun, every rank owns its own 4096 streams (weak scaling,
 no data-path collective -- streams are independent); barrier + max over ranks for the time.
@@ -146,23 +147,47 @@ def ref_lib():
     if not os.path.exists(path):
         return None
     lib = C.CDLL(path)
-    lib.ref_run_mt.restype = C.c_double
+    lib.ref_batch_create.restype = C.c_void_p
+    lib.ref_batch_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_batch_step.restype = C.c_double
+    lib.ref_batch_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.ref_batch_free.argtypes = [C.c_void_p]
+    lib.ref_synth_pcm.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.c_int]
     return lib
 
 
-def cpu_reference_run(kind, fs, mode, streams, frames, threads):
-    """Times the unmodified reference (oracle/_ref) on `threads` host threads; returns audio-s/s."""
+def cpu_reference_steps(kind, fs, mode, streams, frames_per_step, steps, warmup, threads, first_stream=0,
+                        time_limit=150.0):
+    """The unmodified reference (oracle/_ref) on `threads` host threads, driven like the GPU arm: persistent
+    handles (one per stream, created and initialised once), `warmup` untimed steps, then `steps` timed steps
+    of `frames_per_step` frames over all `streams` streams -- the same frames of the same streams the GPU
+    arm's end-to-end leg times (it alternates the PCM of the first two steps; so does this).  Streams are
+    handed to the threads one at a time from a shared counter.  PCM comes from csrc/pcm_synth.h compiled
+    into the shim: the product library is never loaded.  Returns (audio-s/s, steps actually timed)."""
     import numpy as np
-    import audiosignalprocess_b200 as pkg
     lib = ref_lib()
     if lib is None:
-        return None
+        return None, 0
     fl = fs // 100
-    x = pkg.synth_pcm_host(streams, fs, frames * fl)
-    out = np.zeros_like(x)
-    sec = lib.ref_run_mt(1 if kind == "fixed" else 0, fs, mode, streams, frames, threads,
-                         x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
-    return streams * frames * 0.01 / sec
+    n1 = frames_per_step * fl
+    x = [np.zeros((streams, n1), np.int16) for _ in range(2)]
+    for k in range(2):
+        lib.ref_synth_pcm(x[k].ctypes.data, n1, streams, first_stream, fs, k * n1, n1, 1234, threads)
+    out = np.zeros_like(x[0])
+    b = lib.ref_batch_create(1 if kind == "fixed" else 0, fs, mode, streams, threads)
+    if not b:
+        return None, 0
+    for i in range(warmup):
+        lib.ref_batch_step(b, frames_per_step, x[i & 1].ctypes.data, n1, out.ctypes.data, n1)
+    secs = []
+    t0 = time.time()
+    for i in range(steps):
+        secs.append(lib.ref_batch_step(b, frames_per_step, x[(warmup + i) & 1].ctypes.data, n1, out.ctypes.data, n1))
+        if time.time() - t0 > time_limit:
+            break
+    lib.ref_batch_free(b)
+    return streams * frames_per_step * 0.01 * len(secs) / sum(secs), len(secs)
 
 
 def tick_roofline(a, pkg, lib, torch, dev, stream, kind):
@@ -329,27 +354,18 @@ def main():
         if rank != 0:
             return 0
         cores = os.cpu_count() or 1
-        # bounded sample of the same workload: cores*32 streams, F frames per step (a few seconds in all)
-        streams = min(a.streams, cores * 32)
-        for _ in range(min(a.warmup, 1)):
-            cpu_reference_run(kind, a.fs, a.mode, streams, F, cores)
-        t0 = time.time()
-        vals = []
-        for _ in range(a.steps):
-            v = cpu_reference_run(kind, a.fs, a.mode, streams, F, cores)
-            if v is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libns_ref.so missing"}))
-                return 0
-            vals.append(v)
-            if time.time() - t0 > 120:
-                break
-        value = len(vals) / sum(1.0 / v for v in vals)
-        sample = "%d streams x %d frames per step, %d steps, reference C (gcc -O2), %d pthreads" % (
-            streams, F, len(vals), cores)
+        # the GPU arm's own workload: every stream, persistent handles, the same warm-up, the same frames
+        value, done = cpu_reference_steps(kind, a.fs, a.mode, a.streams, F, a.steps, a.warmup, cores)
+        if value is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libns_ref.so missing"}))
+            return 0
+        sample = ("%d streams x %d frames per step, %d timed steps after %d warm-up steps on persistent handles, "
+                  "unmodified reference C (gcc -O2, oracle/Makefile), %d pthreads taking one stream at a time" % (
+                      a.streams, F, done, a.warmup, cores))
         print(json.dumps({
             "impl": "reference", "metric": "ns_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
-            "n_gpus": a.gpus, "steps": len(vals), "warmup": min(a.warmup, 1),
-            "ms_per_step": 1e3 * streams * F * 0.01 / value, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": a.gpus, "steps": done, "warmup": a.warmup,
+            "ms_per_step": 1e3 * a.streams * F * 0.01 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if not a.fixed else "int16/int32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -492,15 +508,14 @@ def main():
         cpu = None
         if not a.no_cpu:
             cores = os.cpu_count() or 1
-            # ~15-25 core-seconds of CPU work: 24 streams per core, 60 s of audio each (the configuration's
-            # duration); the reference runs ~900 audio-s/s per core on the box's hosts
-            streams = cores * 24
-            frames = 6000 if a.fs <= 16000 else 2000
-            v = cpu_reference_run(kind, a.fs, a.mode, streams, frames, cores)
+            # the same workload through the unmodified reference: every stream, persistent handles, the same
+            # warm-up steps, then as many of the timed steps as fit ~15 s (the reference runs ~1000 audio-s/s per core)
+            c_steps = max(4, min(a.steps, int(15.0 * 1000.0 * cores / (a.streams * F * 0.01 * (3.0 if a.fs > 16000 else 1.0)))))
+            v, done = cpu_reference_steps(kind, a.fs, a.mode, a.streams, F, c_steps, a.warmup, cores, first_stream=rank * a.streams)
             if v is not None:
                 cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference",
-                       "sample": "%d streams x %d frames (%.0f s of audio each), %d pthreads, one stream per core at a time"
-                                 % (streams, frames, frames * 0.01, cores)}
+                       "sample": "%d streams x %d frames per step, %d timed steps after %d warm-up steps on persistent handles, "
+                                 "%d pthreads taking one stream at a time" % (a.streams, F, done, a.warmup, cores)}
         tick = None
         if world == 1 and not a.no_tick and F != 1:
             del pcm_in, pcm_out

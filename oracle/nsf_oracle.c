@@ -3,12 +3,12 @@
  * CPU restatement of the float noise suppressor WebRtcNs_Analyze +
  * WebRtcNs_Process (one stream, scalar C), written from the reference's
  * algorithm: same operations in the same order in single precision with the
- * reference's double-precision libm calls, but our own code and our own FFT
- * (a plain radix-2 complex transform plus the real-input split, instead of the
- * reference's table-driven Ooura rdft).  Because the FFT rounds differently the
- * output is not bit-identical to the reference; it is pinned against the
- * compiled reference (oracle/_ref) within the float tolerance of BASELINE.json
- * in tests/test_oracle_pinning.py and against tests/golden/.
+ * reference's double-precision libm calls, including the rounding order of its
+ * real FFT (restated below, not transcribed).  The float suppressor branches on
+ * comparisons that are decided by the last bit of log|X[k]|, so "same order"
+ * is what parity means here: this oracle is pinned BIT FOR BIT against the
+ * compiled reference (oracle/_ref) in tests/test_oracle_pinning.py and against
+ * tests/golden/.
  *
  * Reference (root WebRtc_AMP_Port/webrtc/modules/audio_processing/ns/):
  *   state, init, policy            ns_core.h:52-114, ns_core.c:23-214, 1013-1041
@@ -43,8 +43,11 @@ struct NsfOracle {
   float signal_energy, sum_magn, white_level, init_magn[NB_MAX], pink_num, pink_exp;
   float parametric[NB_MAX], speech_prob[NB_MAX];
   int hist_lrt[1000], hist_flat[1000], hist_diff[1000];
-  float tw_re[ANA_MAX / 2], tw_im[ANA_MAX / 2];   /* e^{+2 pi i k / ana} */
+  float fw_re[ANA_MAX / 8], fw_im[ANA_MAX / 8];   /* quarter-circle twiddles, bit-reversed order */
+  float fc[ANA_MAX / 4 + 1];                      /* half-cosine table of the real split */
 };
+
+static void fft_tables(NsfOracle* s);
 
 NsfOracle* nsf_oracle_create(void) { return (NsfOracle*)calloc(1, sizeof(NsfOracle)); }
 void nsf_oracle_free(NsfOracle* s) { free(s); }
@@ -76,10 +79,7 @@ int nsf_oracle_init(NsfOracle* s, uint32_t fs) {
     double v = i < rise ? sin(pi * i / (2.0 * rise)) : (i <= s->ana - rise ? 1.0 : sin(pi * (s->ana - i) / (2.0 * rise)));
     s->window[i] = (float)(floor(v * 1e8 + 0.5) / 1e8);
   }
-  for (i = 0; i < s->ana / 2; ++i) {
-    s->tw_re[i] = (float)cos(2.0 * pi * i / s->ana);
-    s->tw_im[i] = (float)sin(2.0 * pi * i / s->ana);
-  }
+  fft_tables(s);
   for (i = 0; i < 3 * NB_MAX; ++i) {
     s->lquantile[i] = 8.f;
     s->density[i] = 0.3f;
@@ -110,76 +110,279 @@ float nsf_oracle_prior_speech_probability(const NsfOracle* s) {
   return (!s || !s->inited) ? -1.f : s->prior_speech_prob;
 }
 
-/* ---- FFT: n/2-point complex radix-2 (exponent sign `sgn`) + real split ------ */
-static void cfft(float* re, float* im, int n, int sgn, const float* twr, const float* twi, int tw_n) {
-  int i, j = 0, len;
-  for (i = 1; i < n; ++i) {
-    int bit = n >> 1;
-    for (; j & bit; bit >>= 1) j ^= bit;
-    j ^= bit;
-    if (i < j) {
-      float t = re[i]; re[i] = re[j]; re[j] = t;
-      t = im[i]; im[i] = im[j]; im[j] = t;
+/* ---- real FFT pair in the operation order of the reference's Ooura rdft ---------------------
+ * (utility/fft4g.c:324-361 as ns_core.c:886-944 calls it).  Float addition and multiplication are
+ * not associative, and the noise tracker branches on log|X[k]| to the last bit, so this oracle
+ * reproduces the reference's transform rounding for rounding; it is restated, not transcribed:
+ *   - the n/2 complex points are put in bit-reversed order (what bitrv2, fft4g.c:693, amounts to);
+ *   - radix-4 passes over strides 1, 4, 16 (cft1st :1002 is the stride-1 case of cftmdl :1107): the
+ *     four points of a butterfly are x[j + {0,1,2,3} * stride]; group g = j / (4 * stride) decides
+ *     the three twiddles applied to the butterfly's OUTPUTS (tw_group below), with the sums formed
+ *     as (a0 + a1) + (a2 + a3) etc. exactly as the reference forms them;
+ *   - a last pass without twiddles: radix-2 for 128 complex points, radix-4 for 64 (cftfsub :902,
+ *     cftbsub :952 -- the inverse runs the same twiddled passes on the conjugate and conjugates
+ *     back inside this last pass);
+ *   - the real-input split (rftfsub :1234 / rftbsub :1259) with the half-cosine table of makect :671.
+ * Twiddles: W[q], q < n/8, is the quarter-circle table of makewt (:642) -- (cos, sin)(pi q / (n/4)) with
+ * the angle formed in float as the reference forms it -- read in bit-reversed order.
+ * Pinned bit for bit against WebRtc_rdft itself (oracle/_ref hook ref_rdft) in tests/test_oracle_pinning.py. */
+static unsigned bit_reverse(unsigned v, int bits) {
+  unsigned r = 0;
+  int b;
+  for (b = 0; b < bits; ++b) r |= ((v >> b) & 1u) << (bits - 1 - b);
+  return r;
+}
+static int ilog2(int v) {
+  int b = 0;
+  while ((1 << b) < v) ++b;
+  return b;
+}
+
+static void fft_tables(NsfOracle* s) {
+  const int n = s->ana, nw = n >> 2, nwh = nw >> 1, nq = nw >> 1, qbits = ilog2(nq);
+  const float delta = (float)atan(1.0) / (float)nwh;
+  float w[ANA_MAX / 4];
+  int j, q;
+  w[0] = 1.f;
+  w[1] = 0.f;
+  w[nwh] = (float)cos((double)(delta * (float)nwh));
+  w[nwh + 1] = w[nwh];
+  for (j = 2; j < nwh; j += 2) {
+    const float ang = delta * (float)j;
+    const float x = (float)cos((double)ang), y = (float)sin((double)ang);
+    w[j] = x;
+    w[j + 1] = y;
+    w[nw - j] = y;
+    w[nw - j + 1] = x;
+  }
+  for (q = 0; q < nq; ++q) {
+    const unsigned r = bit_reverse((unsigned)q, qbits);
+    s->fw_re[q] = w[2 * r];
+    s->fw_im[q] = w[2 * r + 1];
+  }
+  /* half-cosine table of the real split: c[j] = cos(pi j / (n/2)) / 2, c[nc - j] = sin(...) / 2 */
+  {
+    const int nc = n >> 2, nch = nc >> 1;
+    const float d2 = (float)atan(1.0) / (float)nch;
+    s->fc[0] = (float)cos((double)(d2 * (float)nch));
+    s->fc[nch] = 0.5f * s->fc[0];
+    for (j = 1; j < nch; ++j) {
+      const float ang = d2 * (float)j;
+      s->fc[j] = 0.5f * (float)cos((double)ang);
+      s->fc[nc - j] = 0.5f * (float)sin((double)ang);
     }
   }
-  for (len = 2; len <= n; len <<= 1) {
-    const int half = len >> 1, step = tw_n / len;
-    for (i = 0; i < n; i += len) {
-      for (j = 0; j < half; ++j) {
-        const float wr = twr[j * step], wi = sgn > 0 ? twi[j * step] : -twi[j * step];
-        const float xr = re[i + j + half], xi = im[i + j + half];
-        const float tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
-        re[i + j + half] = re[i + j] - tr;
-        im[i + j + half] = im[i + j] - ti;
-        re[i + j] += tr;
-        im[i + j] += ti;
+}
+
+typedef struct { float r1, i1, r2, i2, r3, i3; int diag; } TwGroup;
+
+/* Twiddles of butterfly group g (any radix-4 pass): point 1 (offset stride) gets w1, point 2 w2, point 3 w3.
+ * g = 1 is the reference's pi/4 case, which multiplies sums instead of summing products (diag). */
+static TwGroup tw_group(const NsfOracle* s, int g) {
+  TwGroup t = {1.f, 0.f, 1.f, 0.f, 1.f, 0.f, 0};
+  const int p = g >> 1;
+  float ar, ai;
+  if (g == 0) return t;
+  ar = s->fw_re[p];
+  ai = s->fw_im[p];
+  if ((g & 1) == 0) {
+    t.r1 = s->fw_re[2 * p];
+    t.i1 = s->fw_im[2 * p];
+    t.r2 = ar;
+    t.i2 = ai;
+    t.r3 = t.r1 - 2.f * ai * t.i1;
+    t.i3 = 2.f * ai * t.r1 - t.i1;
+  } else {
+    t.r1 = s->fw_re[2 * p + 1];
+    t.i1 = s->fw_im[2 * p + 1];
+    t.r2 = -ai;
+    t.i2 = ar;
+    t.r3 = t.r1 - 2.f * ar * t.i1;
+    t.i3 = 2.f * ar * t.r1 - t.i1;
+    t.diag = g == 1;
+  }
+  return t;
+}
+
+/* the twiddled radix-4 passes shared by both directions, in place on bit-reversed data */
+static int fft_twiddled_passes(const NsfOracle* s, float* re, float* im, int nc) {
+  int l = 1, first = 1;
+  while (first || (l << 2) < nc) {
+    const int m = l << 2;
+    int g, j;
+    first = 0;
+    for (g = 0; g < nc / m; ++g) {
+      const TwGroup t = tw_group(s, g);
+      for (j = g * m; j < g * m + l; ++j) {
+        const int j1 = j + l, j2 = j1 + l, j3 = j2 + l;
+        const float x0r = re[j] + re[j1], x0i = im[j] + im[j1];
+        const float x1r = re[j] - re[j1], x1i = im[j] - im[j1];
+        const float x2r = re[j2] + re[j3], x2i = im[j2] + im[j3];
+        const float x3r = re[j2] - re[j3], x3i = im[j2] - im[j3];
+        const float dr = x0r - x2r, di = x0i - x2i;
+        const float yr = x1r - x3i, yi = x1i + x3r;
+        const float zr = x1r + x3i, zi = x1i - x3r;
+        re[j] = x0r + x2r;
+        im[j] = x0i + x2i;
+        re[j2] = t.r2 * dr - t.i2 * di;
+        im[j2] = t.r2 * di + t.i2 * dr;
+        if (t.diag) {
+          re[j1] = t.r1 * (yr - yi);
+          im[j1] = t.r1 * (yr + yi);
+          re[j3] = t.r1 * (-zi - zr);
+          im[j3] = t.r1 * (-zi + zr);
+        } else {
+          re[j1] = t.r1 * yr - t.i1 * yi;
+          im[j1] = t.r1 * yi + t.i1 * yr;
+          re[j3] = t.r3 * zr - t.i3 * zi;
+          im[j3] = t.r3 * zi + t.i3 * zr;
+        }
       }
     }
+    l = m;
+  }
+  return l;
+}
+
+/* a[0..n): in = time samples, out = the reference's packed spectrum (a[0] = X[0], a[1] = X[n/2],
+ * a[2k], a[2k+1] = Re, Im X[k]; X[k] = sum_j x[j] e^{+2 pi i jk/n}) */
+static void rdft_forward(const NsfOracle* s, float* a) {
+  const int n = s->ana, nc = n / 2, bits = ilog2(nc), ncq = n >> 2;
+  float re[ANA_MAX / 2], im[ANA_MAX / 2];
+  int j, l;
+  for (j = 0; j < nc; ++j) {
+    const unsigned r = bit_reverse((unsigned)j, bits);
+    re[j] = a[2 * r];
+    im[j] = a[2 * r + 1];
+  }
+  l = fft_twiddled_passes(s, re, im, nc);
+  if ((l << 2) == nc) {
+    for (j = 0; j < l; ++j) {
+      const int j1 = j + l, j2 = j1 + l, j3 = j2 + l;
+      const float x0r = re[j] + re[j1], x0i = im[j] + im[j1];
+      const float x1r = re[j] - re[j1], x1i = im[j] - im[j1];
+      const float x2r = re[j2] + re[j3], x2i = im[j2] + im[j3];
+      const float x3r = re[j2] - re[j3], x3i = im[j2] - im[j3];
+      re[j] = x0r + x2r;  im[j] = x0i + x2i;
+      re[j2] = x0r - x2r; im[j2] = x0i - x2i;
+      re[j1] = x1r - x3i; im[j1] = x1i + x3r;
+      re[j3] = x1r + x3i; im[j3] = x1i - x3r;
+    }
+  } else {
+    for (j = 0; j < l; ++j) {
+      const int j1 = j + l;
+      const float dr = re[j] - re[j1], di = im[j] - im[j1];
+      re[j] += re[j1];
+      im[j] += im[j1];
+      re[j1] = dr;
+      im[j1] = di;
+    }
+  }
+  for (j = 1; j < nc / 2; ++j) {
+    const int k = nc - j;
+    const float wkr = 0.5f - s->fc[ncq - j], wki = s->fc[j];
+    const float xr = re[j] - re[k], xi = im[j] + im[k];
+    const float yr = wkr * xr - wki * xi, yi = wkr * xi + wki * xr;
+    re[j] -= yr;
+    im[j] -= yi;
+    re[k] += yr;
+    im[k] -= yi;
+  }
+  {
+    const float d = re[0] - im[0];
+    re[0] += im[0];
+    im[0] = d;
+  }
+  for (j = 0; j < nc; ++j) {
+    a[2 * j] = re[j];
+    a[2 * j + 1] = im[j];
   }
 }
 
-/* X[k] = sum_j x[j] e^{+2 pi i jk/n}, k = 0..n/2 (the sign convention of the
- * reference's rdft, checked numerically in tests/test_oracle_pinning.py) */
-static void rfft_fwd(const NsfOracle* s, const float* x, float* xr, float* xi) {
-  const int n = s->ana, h = n / 2;
-  float zr[ANA_MAX / 2], zi[ANA_MAX / 2];
+/* inverse of the above, unscaled (the caller applies 2/n, ns_core.c:941-943) */
+static void rdft_backward(const NsfOracle* s, float* a) {
+  const int n = s->ana, nc = n / 2, bits = ilog2(nc), ncq = n >> 2;
+  float re[ANA_MAX / 2], im[ANA_MAX / 2], tr[ANA_MAX / 2] = {0.f}, ti[ANA_MAX / 2] = {0.f};
+  int j, l;
+  for (j = 0; j < nc; ++j) {
+    tr[j] = a[2 * j];
+    ti[j] = a[2 * j + 1];
+  }
+  ti[0] = 0.5f * (tr[0] - ti[0]);
+  tr[0] -= ti[0];
+  ti[0] = -ti[0];
+  for (j = 1; j < nc / 2; ++j) {
+    const int k = nc - j;
+    const float wkr = 0.5f - s->fc[ncq - j], wki = s->fc[j];
+    const float xr = tr[j] - tr[k], xi = ti[j] + ti[k];
+    const float yr = wkr * xr + wki * xi, yi = wkr * xi - wki * xr;
+    tr[j] -= yr;
+    ti[j] = yi - ti[j];
+    tr[k] += yr;
+    ti[k] = yi - ti[k];
+  }
+  ti[nc / 2] = -ti[nc / 2];
+  for (j = 0; j < nc; ++j) {
+    const unsigned r = bit_reverse((unsigned)j, bits);
+    re[j] = tr[r];
+    im[j] = ti[r];
+  }
+  l = fft_twiddled_passes(s, re, im, nc);
+  if ((l << 2) == nc) {
+    for (j = 0; j < l; ++j) {
+      const int j1 = j + l, j2 = j1 + l, j3 = j2 + l;
+      const float x0r = re[j] + re[j1], x0i = -im[j] - im[j1];
+      const float x1r = re[j] - re[j1], x1i = -im[j] + im[j1];
+      const float x2r = re[j2] + re[j3], x2i = im[j2] + im[j3];
+      const float x3r = re[j2] - re[j3], x3i = im[j2] - im[j3];
+      re[j] = x0r + x2r;  im[j] = x0i - x2i;
+      re[j2] = x0r - x2r; im[j2] = x0i + x2i;
+      re[j1] = x1r - x3i; im[j1] = x1i - x3r;
+      re[j3] = x1r + x3i; im[j3] = x1i + x3r;
+    }
+  } else {
+    for (j = 0; j < l; ++j) {
+      const int j1 = j + l;
+      const float dr = re[j] - re[j1], di = -im[j] + im[j1];
+      re[j] += re[j1];
+      im[j] = -im[j] - im[j1];
+      re[j1] = dr;
+      im[j1] = di;
+    }
+  }
+  for (j = 0; j < nc; ++j) {
+    a[2 * j] = re[j];
+    a[2 * j + 1] = im[j];
+  }
+}
+
+/* FFT() of ns_core.c:886-911 */
+static void rfft_fwd(const NsfOracle* s, float* x, float* xr, float* xi) {
+  const int h = s->ana / 2;
   int k;
-  for (k = 0; k < h; ++k) {
-    zr[k] = x[2 * k];
-    zi[k] = x[2 * k + 1];
-  }
-  cfft(zr, zi, h, +1, s->tw_re, s->tw_im, n);   /* W_h^j = tw[2j]: step = n/len */
-  for (k = 0; k <= h; ++k) {
-    const int a = k & (h - 1), b = (h - k) & (h - 1);
-    const float er = 0.5f * (zr[a] + zr[b]), ei = 0.5f * (zi[a] - zi[b]);
-    const float orr = 0.5f * (zi[a] + zi[b]), oi = -0.5f * (zr[a] - zr[b]);
-    const float wr = k == h ? -1.f : s->tw_re[k], wi = k == h ? 0.f : s->tw_im[k];
-    xr[k] = er + (orr * wr - oi * wi);
-    xi[k] = ei + (orr * wi + oi * wr);
-  }
+  rdft_forward(s, x);
   xi[0] = 0.f;
+  xr[0] = x[0];
   xi[h] = 0.f;
+  xr[h] = x[1];
+  for (k = 1; k < h; ++k) {
+    xr[k] = x[2 * k];
+    xi[k] = x[2 * k + 1];
+  }
 }
 
-/* inverse of the above including the 2/n scaling of ns_core.c:941-943 */
+/* IFFT() of ns_core.c:923-944 including the 2/n scaling */
 static void rfft_inv(const NsfOracle* s, const float* xr, const float* xi, float* x) {
   const int n = s->ana, h = n / 2;
-  float zr[ANA_MAX / 2], zi[ANA_MAX / 2];
-  const float sc = 2.f / (float)n;
   int k;
-  for (k = 0; k < h; ++k) {
-    const float er = 0.5f * (xr[k] + xr[h - k]), ei = 0.5f * (xi[k] - xi[h - k]);
-    const float dr = 0.5f * (xr[k] - xr[h - k]), di = 0.5f * (xi[k] + xi[h - k]);
-    const float wr = s->tw_re[k], wi = s->tw_im[k];
-    const float orr = dr * wr + di * wi, oi = di * wr - dr * wi;
-    zr[k] = er - oi;
-    zi[k] = ei + orr;
+  x[0] = xr[0];
+  x[1] = xr[h];
+  for (k = 1; k < h; ++k) {
+    x[2 * k] = xr[k];
+    x[2 * k + 1] = xi[k];
   }
-  cfft(zr, zi, h, -1, s->tw_re, s->tw_im, n);
-  for (k = 0; k < h; ++k) {
-    x[2 * k] = zr[k] * sc;
-    x[2 * k + 1] = zi[k] * sc;
-  }
+  rdft_backward(s, x);
+  for (k = 0; k < n; ++k) x[k] *= 2.f / (float)n;
 }
 
 static void push(float* buf, const float* frame, int frame_len, int buf_len) {

@@ -13,6 +13,11 @@
 //   ref_nsx_run     fixed NSx (WebRtcNsx_Process),                   8/16/32/48 kHz
 //   ref_ns_run_mt / ref_nsx_run_mt   same over many streams with pthreads
 //                   (the CPU baseline of bench.py)
+//   ref_batch_*     persistent handles + a thread pool: the CPU arm of bench.py (handles live across
+//                   steps like the GPU arm's, streams handed to threads dynamically)
+//   ref_ns_trace    float NS with the per-frame decision state copied out of the reference struct
+//   ref_rdft        WebRtc_rdft itself (the oracle's FFT restatement is pinned bit for bit against it)
+//   ref_synth_pcm   csrc/pcm_synth.h on the host, so that the reference arm never loads the product library
 //   ref_qmf_* / ref_resample_* / ref_spl_*  primitive hooks for the KATs.
 #include <pthread.h>
 #include <stdint.h>
@@ -29,6 +34,11 @@
 #include "webrtc/modules/audio_processing/audio_buffer.h"
 #include "webrtc/modules/audio_processing/ns/include/noise_suppression.h"
 #include "webrtc/modules/audio_processing/ns/include/noise_suppression_x.h"
+extern "C" {
+#include "webrtc/modules/audio_processing/ns/ns_core.h"        // state trace (read-only) for the parity triage
+#include "webrtc/modules/audio_processing/utility/fft4g.h"     // WebRtc_rdft hook: pins the oracle's FFT restatement
+}
+#include "../audiosignalprocess_b200/csrc/pcm_synth.h"         // our synthetic-PCM generator (integer only, header only)
 
 using webrtc::AudioBuffer;
 
@@ -187,6 +197,241 @@ double ref_run_mt(int fixed, int fs, int mode, int nstreams, int nframes, int nt
   for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+// ---- persistent batch: the CPU arm of bench.py --------------------------------------------------
+// One reference handle (and, at 32/48 kHz, one AudioBuffer) per stream, created once and kept
+// across steps exactly like the GPU arm keeps its streams (test_ns_module.cpp:62-109: one handle,
+// one loop).  A pool of threads started once takes streams one at a time from a shared counter
+// ("one stream per core at a time"), so a silent stream class cannot idle a thread while another
+// thread still holds a queue of expensive ones.
+struct RefBatch {
+  int fixed, fs, mode, n, nthreads;
+  std::vector<void*> handles;
+  std::vector<AudioBuffer*> bufs;     // 32/48 kHz only
+  std::vector<pthread_t> threads;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_go, cv_done;
+  unsigned long long generation;
+  int running, quit;
+  // the step in flight
+  int frames;
+  const int16_t* in;
+  int16_t* out;
+  size_t in_stride, out_stride;
+  volatile int next;
+};
+
+static void RefBatchStream(RefBatch* b, int s) {
+  const int n = FrameLen(b->fs);
+  const int16_t* in = b->in + (size_t)s * b->in_stride;
+  int16_t* out = b->out + (size_t)s * b->out_stride;
+  if (b->fs <= 16000) {
+    if (b->fixed) {
+      NsxHandle* h = (NsxHandle*)b->handles[s];
+      for (int f = 0; f < b->frames; ++f) {
+        const short* inb[1] = {in + (size_t)f * n};
+        short* outb[1] = {out + (size_t)f * n};
+        WebRtcNsx_Process(h, inb, 1, outb);
+      }
+    } else {
+      NsHandle* h = (NsHandle*)b->handles[s];
+      float fin[160], fout[160];
+      for (int f = 0; f < b->frames; ++f) {
+        for (int i = 0; i < n; ++i) fin[i] = (float)in[(size_t)f * n + i];
+        const float* inb[1] = {fin};
+        float* outb[1] = {fout};
+        WebRtcNs_Analyze(h, fin);
+        WebRtcNs_Process(h, inb, 1, outb);
+        for (int i = 0; i < n; ++i) out[(size_t)f * n + i] = RoundToS16(fout[i]);
+      }
+    }
+    return;
+  }
+  AudioBuffer& ab = *b->bufs[s];
+  for (int f = 0; f < b->frames; ++f) {
+    memcpy(ab.data(0), in + (size_t)f * n, sizeof(int16_t) * n);
+    ab.SplitIntoFrequencyBands();
+    if (b->fixed) {
+      WebRtcNsx_Process((NsxHandle*)b->handles[s], ab.split_bands_const(0), ab.num_bands(), ab.split_bands(0));
+    } else {
+      NsHandle* h = (NsHandle*)b->handles[s];
+      WebRtcNs_Analyze(h, ab.split_bands_const_f(0)[webrtc::kBand0To8kHz]);
+      WebRtcNs_Process(h, ab.split_bands_const_f(0), ab.num_bands(), ab.split_bands_f(0));
+    }
+    ab.MergeFrequencyBands();
+    memcpy(out + (size_t)f * n, ab.data_const(0), sizeof(int16_t) * n);
+  }
+}
+
+static void* RefBatchWorker(void* p) {
+  RefBatch* b = (RefBatch*)p;
+  unsigned long long seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&b->mu);
+    while (!b->quit && b->generation == seen) pthread_cond_wait(&b->cv_go, &b->mu);
+    if (b->quit) { pthread_mutex_unlock(&b->mu); return NULL; }
+    seen = b->generation;
+    pthread_mutex_unlock(&b->mu);
+    for (;;) {
+      const int s = __sync_fetch_and_add(&b->next, 1);
+      if (s >= b->n) break;
+      RefBatchStream(b, s);
+    }
+    pthread_mutex_lock(&b->mu);
+    if (--b->running == 0) pthread_cond_signal(&b->cv_done);
+    pthread_mutex_unlock(&b->mu);
+  }
+}
+
+void ref_batch_free(void* p);
+
+void* ref_batch_create(int fixed, int fs, int mode, int nstreams, int nthreads) {
+  if (nstreams <= 0) return NULL;
+  if (nthreads < 1) nthreads = 1;
+  RefBatch* b = new RefBatch();
+  b->fixed = fixed; b->fs = fs; b->mode = mode; b->n = nstreams; b->nthreads = nthreads;
+  b->generation = 0; b->running = 0; b->quit = 0; b->next = 0;
+  pthread_mutex_init(&b->mu, NULL);
+  pthread_cond_init(&b->cv_go, NULL);
+  pthread_cond_init(&b->cv_done, NULL);
+  b->handles.assign(nstreams, (void*)NULL);
+  bool ok = true;
+  for (int s = 0; s < nstreams && ok; ++s) {
+    if (fixed) {
+      NsxHandle* h = NULL;
+      ok = WebRtcNsx_Create(&h) == 0 && WebRtcNsx_Init(h, (uint32_t)fs) == 0 && WebRtcNsx_set_policy(h, mode) == 0;
+      b->handles[s] = h;
+    } else {
+      NsHandle* h = NULL;
+      ok = WebRtcNs_Create(&h) == 0 && WebRtcNs_Init(h, (uint32_t)fs) == 0 && WebRtcNs_set_policy(h, mode) == 0;
+      b->handles[s] = h;
+    }
+    if (fs > 16000) b->bufs.push_back(new AudioBuffer(FrameLen(fs), 1, FrameLen(fs), 1, FrameLen(fs)));
+  }
+  if (!ok) { ref_batch_free(b); return NULL; }
+  b->threads.resize(nthreads);
+  for (int t = 0; t < nthreads; ++t)
+    if (pthread_create(&b->threads[t], NULL, RefBatchWorker, b) != 0) { b->threads.resize(t); ref_batch_free(b); return NULL; }
+  return b;
+}
+
+// One step: `frames` 10 ms frames of every stream.  in/out: [stream][stride] int16 (out may alias in).
+// Returns the wall seconds of the step (CLOCK_MONOTONIC around wake-up .. last thread done).
+double ref_batch_step(void* p, int frames, const int16_t* in, size_t in_stride, int16_t* out, size_t out_stride) {
+  RefBatch* b = (RefBatch*)p;
+  if (!b || frames < 0) return -1.0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_mutex_lock(&b->mu);
+  b->frames = frames; b->in = in; b->out = out; b->in_stride = in_stride; b->out_stride = out_stride;
+  b->next = 0;
+  b->running = (int)b->threads.size();
+  b->generation++;
+  pthread_cond_broadcast(&b->cv_go);
+  while (b->running > 0) pthread_cond_wait(&b->cv_done, &b->mu);
+  pthread_mutex_unlock(&b->mu);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+void ref_batch_free(void* p) {
+  RefBatch* b = (RefBatch*)p;
+  if (!b) return;
+  pthread_mutex_lock(&b->mu);
+  b->quit = 1;
+  pthread_cond_broadcast(&b->cv_go);
+  pthread_mutex_unlock(&b->mu);
+  for (size_t t = 0; t < b->threads.size(); ++t) pthread_join(b->threads[t], NULL);
+  for (size_t s = 0; s < b->handles.size(); ++s) {
+    if (!b->handles[s]) continue;
+    if (b->fixed) WebRtcNsx_Free((NsxHandle*)b->handles[s]);
+    else WebRtcNs_Free((NsHandle*)b->handles[s]);
+  }
+  for (size_t s = 0; s < b->bufs.size(); ++s) delete b->bufs[s];
+  pthread_mutex_destroy(&b->mu);
+  pthread_cond_destroy(&b->cv_go);
+  pthread_cond_destroy(&b->cv_done);
+  delete b;
+}
+
+// Synthetic PCM of streams [first_stream, first_stream + nstreams) on `nthreads` host threads
+// (csrc/pcm_synth.h is a pure function of (seed, stream, fs, n): the same bits as the device generator).
+struct SynthJob { int16_t* dst; size_t stride; int n, tid, nthreads; uint32_t first_stream, fs, first_sample, n_samples, seed; };
+static void* SynthWorker(void* p) {
+  SynthJob* j = (SynthJob*)p;
+  for (int s = j->tid; s < j->n; s += j->nthreads) {
+    int16_t* d = j->dst + (size_t)s * j->stride;
+    for (uint32_t i = 0; i < j->n_samples; ++i) d[i] = pcm_synth_sample(j->seed, j->first_stream + (uint32_t)s, j->fs, j->first_sample + i);
+  }
+  return NULL;
+}
+void ref_synth_pcm(int16_t* dst, size_t stride, int nstreams, uint32_t first_stream, uint32_t fs, uint32_t first_sample,
+                   uint32_t n_samples, uint32_t seed, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  std::vector<pthread_t> th(nthreads);
+  std::vector<SynthJob> jobs(nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    SynthJob j = {dst, stride, nstreams, t, nthreads, first_stream, fs, first_sample, n_samples, seed};
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, SynthWorker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+}
+
+// ---- float NS with the decision state copied out of the reference's struct after every frame ---
+// (8/16 kHz).  Per frame kRefTraceWords floats, bins padded to 129:
+//   [0,387) lquantile[3][129] | [387,774) density[3][129] | quantile | smooth | noisePrev | magnPrevAnalyze |
+//   logLrtTimeAvg | magnAvgPause (6 x 129 from 774) | featureData[7] | priorModelPars[7] | priorSpeechProb |
+//   blockInd | counter[3] | updates | modelUpdatePars[4] | signalEnergy | sumMagn
+int ref_ns_trace_words(void) { return 774 + 6 * 129 + 7 + 7 + 1 + 1 + 3 + 1 + 4 + 2; }
+int ref_ns_trace(int fs, int mode, int nframes, const int16_t* pcm_in, float* out_f32, float* trace) {
+  if (!(fs == 8000 || fs == 16000)) return -1;
+  NsHandle* h = NULL;
+  if (WebRtcNs_Create(&h) != 0) return -1;
+  if (WebRtcNs_Init(h, (uint32_t)fs) != 0 || WebRtcNs_set_policy(h, mode) != 0) {
+    WebRtcNs_Free(h);
+    return -1;
+  }
+  const NoiseSuppressionC* st = (const NoiseSuppressionC*)h;
+  const int n = FrameLen(fs), W = ref_ns_trace_words(), ml = st->magnLen;
+  std::vector<float> in(n), out(n);
+  for (int f = 0; f < nframes; ++f) {
+    for (int i = 0; i < n; ++i) in[i] = (float)pcm_in[(size_t)f * n + i];
+    const float* inb[1] = {in.data()};
+    float* outb[1] = {out.data()};
+    WebRtcNs_Analyze(h, in.data());
+    WebRtcNs_Process(h, inb, 1, outb);
+    if (out_f32) memcpy(out_f32 + (size_t)f * n, out.data(), sizeof(float) * n);
+    float* t = trace + (size_t)f * W;
+    memset(t, 0, sizeof(float) * W);
+    for (int s = 0; s < 3; ++s)
+      for (int i = 0; i < ml; ++i) {
+        t[s * 129 + i] = st->lquantile[s * ml + i];
+        t[387 + s * 129 + i] = st->density[s * ml + i];
+      }
+    const float* per_bin[6] = {st->quantile, st->smooth, st->noisePrev, st->magnPrevAnalyze, st->logLrtTimeAvg, st->magnAvgPause};
+    for (int a = 0; a < 6; ++a) memcpy(t + 774 + a * 129, per_bin[a], sizeof(float) * ml);
+    float* u = t + 774 + 6 * 129;
+    memcpy(u, st->featureData, sizeof(float) * 7);
+    memcpy(u + 7, st->priorModelPars, sizeof(float) * 7);
+    u[14] = st->priorSpeechProb;
+    u[15] = (float)st->blockInd;
+    for (int s = 0; s < 3; ++s) u[16 + s] = (float)st->counter[s];
+    u[19] = (float)st->updates;
+    for (int k = 0; k < 4; ++k) u[20 + k] = (float)st->modelUpdatePars[k];
+    u[24] = st->signalEnergy;
+    u[25] = st->sumMagn;
+  }
+  WebRtcNs_Free(h);
+  return 0;
+}
+
+// The reference's real FFT itself (utility/fft4g.c:324) with fresh work arrays, as ns_core.c:886-944 calls it.
+void ref_rdft(int n, int isgn, float* a) {
+  std::vector<int> ip(2 + 64, 0);        // IP_LENGTH of ns_core.h covers n <= 256
+  std::vector<float> w(256, 0.f);
+  WebRtc_rdft(n, isgn, a, ip.data(), w.data());
 }
 
 // ---- primitive hooks for known-answer tests ---------------------------------

@@ -142,3 +142,47 @@ def summarize_parity(results, what, min_strict_frac):
     assert all(r[1] for r in results), "outside the reference's own cross-build envelope: " + line
     assert n_strict >= min_strict_frac * n, "too few streams within the strict tolerance: " + line
     return line
+
+
+# ---- decision state of the float suppressor, reference vs GPU -------------------------------------------
+# The reference struct after a run (oracle/ref_shim.cc ref_ns_trace) and the GPU state slab of a handle
+# (WebRtcNsB200_ExportState; layout csrc/nsf_layout.h behind the 696-byte StateBlobHeader of ns_capi.cu).
+NSF_BLOB_HEADER_BYTES = 696
+NSF_OFF_BINS, NSF_BIN_REC = 548, 12
+
+
+def ref_ns_trace(reflib, fs, mode, pcm):
+    """-> (float out [samples], dict of per-frame arrays: lquantile/density [frames,3,bins], magn, quantile,
+    smooth, noisePrev, logLrt, magnAvgPause [frames,bins], prior [frames])"""
+    lib = reflib.lib
+    fl = fs // 100
+    nfr = len(pcm) // fl
+    nb = 129 if fs == 16000 else 65
+    W = lib.ref_ns_trace_words()
+    tr = np.zeros((nfr, W), np.float32)
+    out = np.zeros(nfr * fl, np.float32)
+    x = np.ascontiguousarray(pcm, np.int16)
+    assert lib.ref_ns_trace(fs, mode, nfr, _ptr(x), _ptr(out), _ptr(tr)) == 0
+    per = tr[:, 774:774 + 6 * 129].reshape(nfr, 6, 129)[:, :, :nb]
+    u = tr[:, 774 + 6 * 129:]
+    return out, {"lquantile": tr[:, 0:387].reshape(nfr, 3, 129)[:, :, :nb], "density": tr[:, 387:774].reshape(nfr, 3, 129)[:, :, :nb],
+                 "quantile": per[:, 0], "smooth": per[:, 1], "noisePrev": per[:, 2], "magn": per[:, 3], "logLrt": per[:, 4],
+                 "magnAvgPause": per[:, 5], "featureData": u[:, 0:7], "priorModelPars": u[:, 7:14], "prior": u[:, 14]}
+
+
+def gpu_nsf_state(lib, handle, fs):
+    """The per-bin records of one float-NS handle: dict like ref_ns_trace's, one frame."""
+    nb = 129 if fs == 16000 else 65
+    size = lib.WebRtcNsB200_StateSize(handle)
+    buf = np.zeros(size, np.uint8)
+    assert lib.WebRtcNsB200_ExportState(handle, _ptr(buf), size) == 0, lib.WebRtcNsB200_LastError()
+    st = buf[NSF_BLOB_HEADER_BYTES:].view(np.float32)
+    rec = st[NSF_OFF_BINS:NSF_OFF_BINS + nb * NSF_BIN_REC].reshape(nb, NSF_BIN_REC)
+    return {"lquantile": rec[:, 0:3].T.copy(), "density": rec[:, 3:6].T.copy(), "quantile": rec[:, 6].copy(),
+            "smooth": rec[:, 7].copy(), "noisePrev": rec[:, 8].copy(), "magn": rec[:, 9].copy(), "logLrt": rec[:, 10].copy(),
+            "magnAvgPause": rec[:, 11].copy(), "featureData": st[16:23].copy(), "priorModelPars": st[8:15].copy(),
+            "prior": float(st[15])}
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32))

@@ -39,8 +39,9 @@ extern "C" {
 // float.  fpl = frames per emulated launch (state round-trips the slab between
 // launches exactly as on the device).  prior_prob: [stream][frame] or NULL
 // (only filled when fpl == 1).
-int emu_nsf_run(int fs, int mode, int nb, int i16, int nstreams, int nframes, int fpl,
-                const void* in, void* out, float* prior_prob) {
+// state_out (optional): [stream][kNsfStateWords] words, the slab of every stream after the last frame.
+int emu_nsf_run_state(int fs, int mode, int nb, int i16, int nstreams, int nframes, int fpl,
+                      const void* in, void* out, float* prior_prob, uint32_t* state_out) {
   const int ana = fs == 8000 ? 128 : 256;
   const int fl = fs == 8000 ? 80 : 160;
   Fn fn = Pick(ana, nb, i16 != 0);
@@ -75,8 +76,16 @@ int emu_nsf_run(int fs, int mode, int nb, int i16, int nstreams, int nframes, in
         prior_prob[(size_t)s * nframes + f0] =
             ((float*)&state[(size_t)slots[s] * kNsfStateWords])[kH_priorSpeechProb];
   }
+  if (state_out)
+    for (int s = 0; s < nstreams; ++s)
+      memcpy(state_out + (size_t)s * kNsfStateWords, &state[(size_t)slots[s] * kNsfStateWords], sizeof(uint32_t) * kNsfStateWords);
   return 0;
 }
+int emu_nsf_run(int fs, int mode, int nb, int i16, int nstreams, int nframes, int fpl,
+                const void* in, void* out, float* prior_prob) {
+  return emu_nsf_run_state(fs, mode, nb, i16, nstreams, nframes, fpl, in, out, prior_prob, NULL);
+}
+int emu_nsf_state_words(void) { return kNsfStateWords; }
 
 // Split mode (float samples): Analyze sees ana[stream][frame][fl], Process sees in[stream][frame][band][fl].
 // The first `fused_frames` frames run through the fused kernel on `in` (ana ignored) so that the

@@ -141,9 +141,11 @@ def test_device_arithmetic_selftest(nslib):
     cases; fdiv() equals IEEE division except for <= 2 per million quotients one ulp off (none worse)."""
     import ctypes as C
     lib = nslib.load_library()
-    st = (C.c_uint64 * 3)()
+    st = (C.c_uint64 * 5)()
     assert lib.WebRtcNsB200_SelfTestStats(1 << 28, st) == 0, lib.WebRtcNsB200_LastError()
-    print("self-test: hard %d, divisions one ulp off %d of %d (%.2e)" % (st[0], st[1], st[2], st[1] / max(1, st[2])))
+    print("self-test: hard %d, divisions one ulp off %d of %d (%.2e), log_rn != (float)log(double) %d of %d (%.2e)" % (
+        st[0], st[1], st[2], st[1] / max(1, st[2]), st[3], st[4], st[3] / max(1, st[4])))
     assert st[0] == 0
     assert st[1] * 1000000 <= st[2] * 2
+    assert st[3] * 100000 <= st[4]
     assert lib.WebRtcNsB200_SelfTest(1 << 24) == 0, lib.WebRtcNsB200_LastError()

@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""Float-NS parity report (GPU box): every float test configuration plus a 256-stream x 60 s set at
+8/16/32/48 kHz, the GPU library against the compiled reference (oracle/_ref/libns_ref.so), with the
+reference compared against ITS OWN FMA-contracted build (libns_ref_fma.so) on the same streams beside it.
+
+  python tools/float_parity_report.py --out profiles/r2_float_parity.md [--quick] [--triage N]
+
+Tolerance (BASELINE.json north_star): per stream max |diff| <= 1e-4 full scale (3.2768 int16 units) and
+SNR of the difference >= 90 dB ("strict").  int16 outputs (32/48 kHz go through the band merge in int16)
+are judged with one LSB of rounding slack, as in tests/conftest.py.
+
+--triage N: for up to N non-strict 8/16 kHz streams, find the first frame whose decision state (the three
+log-quantile trackers and their densities, ns_core.c:236-259) differs from the reference's, and say which
+comparison went the other way and how close its operands were.  Test infrastructure: reads oracle/_ref."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import judge_float, snr_db  # noqa: E402
+
+import audiosignalprocess_b200 as pkg  # noqa: E402
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def load_ref(name):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
+    return C.CDLL(p) if os.path.exists(p) else None
+
+
+REF = load_ref("libns_ref.so")
+REF_FMA = load_ref("libns_ref_fma.so")
+THREADS = os.cpu_count() or 1
+
+
+def synth(n, fs, samples, seed):
+    x = np.zeros((n, samples), np.int16)
+    REF.ref_synth_pcm(ptr(x), samples, n, 0, fs, 0, samples, seed, THREADS)
+    return x
+
+
+def ref_run(lib, fs, mode, x, want_float):
+    """-> [n, samples] float32 (8/16 kHz, want_float) or int16"""
+    n, samples = x.shape
+    frames = samples // (fs // 100)
+    out = np.zeros((n, samples), np.float32 if want_float else np.int16)
+
+    def one(s):
+        if want_float:
+            rc = lib.ref_ns_run(fs, mode, frames, ptr(x[s]), ptr(out[s]), None, None)
+        else:
+            rc = lib.ref_ns_run(fs, mode, frames, ptr(x[s]), None, ptr(out[s]), None)
+        assert rc == 0
+
+    with ThreadPoolExecutor(THREADS) as ex:
+        list(ex.map(one, range(n)))
+    return out
+
+
+def gpu_run(fs, mode, x, want_float, chunks):
+    n, samples = x.shape
+    fl = fs // 100
+    frames = samples // fl
+    b = pkg.NsBatch(n, fs, mode)
+    if want_float:
+        xin = x.astype(np.float32).reshape(n, frames, 1, fl)
+        out = np.zeros((n, frames, 1, fl), np.float32)
+    else:
+        out = np.zeros_like(x)
+    f0, ci = 0, 0
+    while f0 < frames:
+        nf = min(chunks[min(ci, len(chunks) - 1)], frames - f0)
+        if want_float:
+            out[:, f0:f0 + nf] = b.process_bands_f32(np.ascontiguousarray(xin[:, f0:f0 + nf]))
+        else:
+            out[:, f0 * fl:(f0 + nf) * fl] = b.process(np.ascontiguousarray(x[:, f0 * fl:(f0 + nf) * fl]))
+        f0 += nf
+        ci += 1
+    b.close()
+    return out.reshape(n, samples)
+
+
+def first_bad_frame(ref, out, fl, thr=0.5):
+    d = np.abs(out.astype(np.float64) - ref.astype(np.float64)).reshape(-1, fl).max(1)
+    bad = np.nonzero(d > thr)[0]
+    return int(bad[0]) if len(bad) else None
+
+
+def judge_set(ref, out, slack):
+    return [judge_float(ref[s], out[s], slack=slack) for s in range(ref.shape[0])]
+
+
+def summarize(res):
+    n = len(res)
+    return {"strict": sum(1 for r in res if r[0]), "n": n, "envelope": sum(1 for r in res if r[1]),
+            "worst_abs": max(r[2] for r in res), "worst_snr": min(r[3] for r in res),
+            "median_snr": float(np.median([r[3] for r in res]))}
+
+
+# ---- triage ---------------------------------------------------------------------------------------
+HDR_BYTES = 696          # StateBlobHeader of ns_capi.cu
+OFF_BINS, REC = 548, 12  # nsf_layout.h
+
+
+def gpu_state_trace(fs, mode, x1, nframes):
+    """One stream frame by frame through the library, the state slab exported after every frame."""
+    lib = pkg.load_library()
+    fl = fs // 100
+    b = pkg.NsBatch(1, fs, mode)
+    size = lib.WebRtcNsB200_StateSize(b._handles[0])
+    buf = np.zeros(size, np.uint8)
+    nb = 129 if fs == 16000 else 65
+    lq = np.zeros((nframes, 3, nb), np.float32)
+    dn = np.zeros((nframes, 3, nb), np.float32)
+    magn = np.zeros((nframes, nb), np.float32)
+    xin = x1.astype(np.float32).reshape(-1, 1, fl)
+    for f in range(nframes):
+        b.process_bands_f32(np.ascontiguousarray(xin[f:f + 1]).reshape(1, 1, 1, fl))
+        assert lib.WebRtcNsB200_ExportState(b._handles[0], ptr(buf), size) == 0
+        st = buf[HDR_BYTES:].view(np.float32)
+        rec = st[OFF_BINS:OFF_BINS + nb * REC].reshape(nb, REC)
+        lq[f] = rec[:, 0:3].T
+        dn[f] = rec[:, 3:6].T
+        magn[f] = rec[:, 9]
+    b.close()
+    return lq, dn, magn
+
+
+def triage_stream(fs, mode, x1, upto):
+    fl = fs // 100
+    nb = 129 if fs == 16000 else 65
+    W = REF.ref_ns_trace_words()
+    tr = np.zeros((upto, W), np.float32)
+    assert REF.ref_ns_trace(fs, mode, upto, ptr(x1), None, ptr(tr)) == 0
+    r_lq = tr[:, 0:387].reshape(upto, 3, 129)[:, :, :nb]
+    r_dn = tr[:, 387:774].reshape(upto, 3, 129)[:, :, :nb]
+    r_magn = tr[:, 774 + 3 * 129:774 + 4 * 129][:, :nb]
+    g_lq, g_dn, g_magn = gpu_state_trace(fs, mode, x1, upto)
+    # ulp-level drift of lq is expected; a flipped comparison moves lq by a whole tracker step or
+    # changes the density by 1/(counter+1) of 50
+    for f in range(upto):
+        dl = np.abs(g_lq[f] - r_lq[f])
+        dd = np.abs(g_dn[f] - r_dn[f])
+        if dl.max() > 1e-4 or dd.max() > 1e-3:
+            t, k = np.unravel_index(np.argmax(dl if dl.max() > 1e-4 else dd), dl.shape)
+            what = "quantile step direction (lmagn > lquantile, ns_core.c:243)" if dl.max() > 1e-4 else \
+                   "density window (|lmagn - lquantile| < WIDTH, ns_core.c:252)"
+            lm_r = float(np.log(np.float64(r_magn[f, k])))
+            lm_g = float(np.log(np.float64(g_magn[f, k])))
+            prev_lq = float(r_lq[f - 1, t, k]) if f > 0 else 8.0
+            margin = (lm_r - prev_lq) if dl.max() > 1e-4 else (abs(lm_r - float(r_lq[f, t, k])) - 0.01)
+            magn_ulps = int(np.int64(g_magn[f, k].view(np.int32)) - np.int64(r_magn[f, k].view(np.int32)))
+            n_magn_diff = int((g_magn[f] != r_magn[f]).sum())
+            return {"frame": f, "bin": int(k), "tracker": int(t), "comparison": what,
+                    "operand_margin": margin, "lmagn_ref": lm_r, "lmagn_gpu_minus_ref": lm_g - lm_r,
+                    "magn_gpu_minus_ref_ulps": magn_ulps, "bins_with_different_magn_this_frame": n_magn_diff,
+                    "delta_lq": float(dl.max()), "delta_density": float(dd.max())}
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_float_parity.md"))
+    ap.add_argument("--quick", action="store_true", help="64 streams x 12 s instead of 256 x 60 s")
+    ap.add_argument("--triage", type=int, default=8)
+    ap.add_argument("--label", default="")
+    a = ap.parse_args()
+    assert REF is not None, "oracle/_ref/libns_ref.so missing"
+    t_start = time.time()
+    ragged = [1, 2, 7, 40, 250, 10 ** 9]
+    cases = []   # (name, fs, mode, n, frames, seed, want_float, chunks)
+    for fs, mode, frames in [(16000, 2, 1200), (16000, 0, 300), (16000, 1, 300), (16000, 3, 300), (8000, 2, 1200), (8000, 1, 300)]:
+        cases.append(("test_batch_int16 fs=%d mode=%d" % (fs, mode), fs, mode, 8, frames, 1234, False, ragged))
+    for fs, mode in [(16000, 2), (8000, 2), (16000, 0)]:
+        cases.append(("test_batch_float_bands fs=%d mode=%d" % (fs, mode), fs, mode, 8, 1100, 1234, True, [10 ** 9]))
+    cases.append(("test_many_streams 64 x 12 s", 16000, 2, 64, 1200, 777, True, [10 ** 9]))
+    bn, bf = (64, 1200) if a.quick else (256, 6000)
+    for fs in (8000, 16000, 32000, 48000):
+        cases.append(("%d streams x %d s, fs=%d mode=2" % (bn, bf // 100, fs), fs, 2, bn, bf if fs <= 16000 else bf // 2,
+                      4242, fs <= 16000, [100]))
+    rows, triage_rows = [], []
+    budget = a.triage
+    for name, fs, mode, n, frames, seed, want_float, chunks in cases:
+        fl = fs // 100
+        x = synth(n, fs, frames * fl, seed)
+        ref = ref_run(REF, fs, mode, x, want_float)
+        out = gpu_run(fs, mode, x, want_float, chunks)
+        slack = 0.0 if want_float else 1.0
+        res = judge_set(ref, out, slack)
+        g = summarize(res)
+        r = None
+        if REF_FMA is not None:
+            fma = ref_run(REF_FMA, fs, mode, x, want_float)
+            r = summarize(judge_set(ref, fma, slack))
+        bad = [s for s in range(n) if not res[s][0]]
+        firsts = {s: first_bad_frame(ref[s], out[s], fl) for s in bad}
+        rows.append((name, "float" if want_float else "int16", g, r, firsts))
+        print("%-44s GPU %3d/%3d strict, worst %.3f LSB %.1f dB | ref-vs-refFMA %s" % (
+            name, g["strict"], g["n"], g["worst_abs"], g["worst_snr"],
+            "%d/%d, %.3f LSB %.1f dB" % (r["strict"], r["n"], r["worst_abs"], r["worst_snr"]) if r else "n/a"), flush=True)
+        if fs <= 16000:
+            for s in bad:
+                if budget <= 0:
+                    break
+                ff = firsts[s]
+                upto = min(frames, (ff if ff is not None else frames - 1) + 1)
+                t = triage_stream(fs, mode, x[s], upto)
+                budget -= 1
+                triage_rows.append((name, s, ff, t))
+                print("   triage stream %d: first frame >0.5 LSB %s -> %s" % (s, ff, json.dumps(t)), flush=True)
+    with open(a.out, "w") as f:
+        f.write("# Float NS parity on the B200: GPU library vs the compiled reference%s\n\n" % (" (%s)" % a.label if a.label else ""))
+        f.write("Made by `tools/float_parity_report.py` on the GPU box (%d host threads, %.0f s).  *strict* = per stream "
+                "max |diff| <= 1e-4 full scale (3.2768 LSB) and SNR of the difference >= 90 dB (BASELINE.json); int16 outputs "
+                "carry one LSB of rounding slack.  The right-hand columns are the unmodified reference against its own "
+                "FMA-contracted build (`oracle/_ref/libns_ref_fma.so`) on the same streams.\n\n" % (THREADS, time.time() - t_start))
+        f.write("| case | output | GPU strict | GPU worst abs (LSB) | GPU worst SNR (dB) | GPU median SNR | ref-vs-refFMA strict | worst abs | worst SNR |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|\n")
+        for name, kind, g, r, firsts in rows:
+            f.write("| %s | %s | %d/%d | %.3f | %.1f | %.1f | %s |\n" % (
+                name, kind, g["strict"], g["n"], g["worst_abs"], g["worst_snr"], g["median_snr"],
+                "%d/%d | %.3f | %.1f" % (r["strict"], r["n"], r["worst_abs"], r["worst_snr"]) if r else "n/a | | "))
+        f.write("\nAll streams inside the envelope gate (SNR >= 55 dB, <= 1e-2 FS): %s\n" % all(g["envelope"] == g["n"] for _, _, g, _, _ in rows))
+        nonstrict = [(name, firsts) for name, _, _, _, firsts in rows if firsts]
+        f.write("\n## Non-strict streams (first frame with |diff| > 0.5 LSB)\n\n")
+        if not nonstrict:
+            f.write("none\n")
+        for name, firsts in nonstrict:
+            f.write("* %s: %s\n" % (name, ", ".join("stream %d @ frame %s" % (s, ff) for s, ff in sorted(firsts.items()))))
+        f.write("\n## Triage: which comparison went the other way first\n\n")
+        if not triage_rows:
+            f.write("nothing to triage\n")
+        for name, s, ff, t in triage_rows:
+            if t is None:
+                f.write("* %s, stream %d (first output frame off: %s): tracker state identical to 1e-4 up to that frame -- not a quantile-tracker flip\n" % (name, s, ff))
+            else:
+                f.write("* %s, stream %d (first output frame off: %s): state leaves the reference at frame %d, bin %d, tracker %d: %s; "
+                        "operand margin %.3g, GPU lmagn - ref lmagn = %.3g (magn differs by %d ulp; %d bins of that frame have a different magn), "
+                        "delta lquantile %.4g, delta density %.4g\n" % (
+                            name, s, ff, t["frame"], t["bin"], t["tracker"], t["comparison"], t["operand_margin"],
+                            t["lmagn_gpu_minus_ref"], t["magn_gpu_minus_ref_ulps"], t["bins_with_different_magn_this_frame"],
+                            t["delta_lq"], t["delta_density"]))
+    print("wrote", a.out)
+    js = {"rows": [{"case": n, "kind": k, "gpu": g, "ref_vs_fma": r, "nonstrict_first_frames": {str(s): ff for s, ff in fr.items()}}
+                   for n, k, g, r, fr in rows]}
+    with open(os.path.splitext(a.out)[0] + ".json", "w") as f:
+        json.dump(js, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
