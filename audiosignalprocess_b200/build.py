@@ -40,16 +40,22 @@ def build_library(force=False, verbose=False):
 
 
 def build_examples():
-    """examples/test_ns_module: the Linux clone of the reference CLI driver, linked against the library."""
-    src = os.path.join(HERE, "..", "examples", "test_ns_module.cpp")
-    exe = os.path.join(HERE, "test_ns_module")
-    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
-        return exe
-    cmd = ["g++", "-O2", "-std=c++11", "-o", exe, src, "-L" + HERE, "-lwebrtc_ns_b200", "-Wl,-rpath,$ORIGIN"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
-    return exe
+    """examples/test_ns_module: the Linux clone of the reference CLI driver; examples/apm_ns_block: the C++ mirror
+    of the author's APM_NS class (include/apm_ns_b200.h) driven block by block.  Both link against the library."""
+    out = []
+    hdrs = [os.path.join(HERE, "..", "include", h) for h in ("webrtc_ns_b200.h", "apm_ns_b200.h")]
+    for name in ("test_ns_module", "apm_ns_block"):
+        src = os.path.join(HERE, "..", "examples", name + ".cpp")
+        exe = os.path.join(HERE, name)
+        out.append(exe)
+        if os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(src), os.path.getmtime(LIB)] +
+                                                               [os.path.getmtime(h) for h in hdrs]):
+            continue
+        cmd = ["g++", "-O2", "-std=c++11", "-Wall", "-o", exe, src, "-L" + HERE, "-lwebrtc_ns_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return out
 
 
 if __name__ == "__main__":

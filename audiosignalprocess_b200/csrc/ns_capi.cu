@@ -104,6 +104,7 @@ struct DeviceCtx {
   size_t stage_elems = 0;
   int16_t* d_bands = nullptr;   // [stream][frame][band][160] scratch for 32/48 kHz
   size_t bands_elems = 0;
+  float* d_single = nullptr;           // single-frame float calls (WebRtcNs_Analyze / WebRtcNs_Process): in | out | ana
   int16_t* d_band_scratch = nullptr;   // 48 kHz: 64 kHz and 32 kHz intermediates
   size_t band_scratch_elems = 0;
   int32_t* d_down_sched = nullptr;     // 48 kHz: resampler schedule of the current launch
@@ -178,8 +179,23 @@ void DrainPending(int dev) {
 // helpers below need not compare 8 bytes per stream again (a one-frame tick over 32768 streams is
 // ~125 us of GPU time; the host side of the call has to stay well below that)
 thread_local bool t_call_is_memo = false;
+// The library switches the calling thread's current device as it works through a call's devices; the caller
+// gets its own back (it decides where handles are created when WebRtcNsB200_SetCreateDevice was not used).
+struct KeepCallerDevice {
+  int saved = -1;
+  KeepCallerDevice() {
+    if (cudaGetDevice(&saved) != cudaSuccess) {
+      saved = -1;
+      cudaGetLastError();
+    }
+  }
+  ~KeepCallerDevice() {
+    if (saved >= 0) cudaSetDevice(saved);
+  }
+};
 // Changes which handles exist or where they live: alone in the library, nothing in flight.
 struct ExclusiveLock {
+  KeepCallerDevice keep;
   std::unique_lock<std::shared_mutex> guard;
   ExclusiveLock() : guard(g_rw) {
     t_call_is_memo = false;
@@ -189,6 +205,7 @@ struct ExclusiveLock {
 // Uses devices: shared with other users, one mutex per device touched (taken in ascending device order
 // when a call spans several).
 struct UseLock {
+  KeepCallerDevice keep;
   std::shared_lock<std::shared_mutex> guard;
   std::vector<std::unique_lock<std::mutex>> held;
   UseLock() : guard(g_rw) { t_call_is_memo = false; }
@@ -870,7 +887,9 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
         if (LaunchNs(d, magic, ana, nb, n, d.d_bands, bands_ss, d.d_bands, bands_ss, nb * 160, 160, f0, nf, s, split) != 0)
           return -1;
       } else {
-        if (LaunchBandStage(nb, bl, bk, f0, nf, s, &g_launches) != 0) return Fail("band stage launch failed");
+        uint64_t launched = 0;
+        if (LaunchBandStage(nb, bl, bk, f0, nf, s, &launched) != 0) return Fail("band stage launch failed");
+        g_launches += launched;
       }
       CU_OK(cudaEventRecord(d.band_events[(size_t)c * nstages + k], s));
       mark(s);
@@ -1280,20 +1299,29 @@ int WaitBatch(uint64_t ticket) {
 
 // Single-stream float call = batch of one over float band frames.
 // ana (optional): [stream][frame][frame_len] band-0 frames for Analyze, stride ana_ss floats.
+// phase (nsf_kernel.cuh): 0 = whole frames; 1 = the Analyze half alone (only `ana` is read, nothing written
+// but state); 2 = the Process half alone on `in`, using what the Analyze call left in the state.
 int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_ss, float* out,
-                    size_t out_ss, int frames, const float* ana = nullptr, size_t ana_ss = 0) {
-  ApiLock lk;
+                    size_t out_ss, int frames, const float* ana = nullptr, size_t ana_ss = 0, int phase = 0) {
+  UseLock lk;
   if (!hv || n <= 0) return Fail("no handles");
+  if (phase == 1 ? !ana : (!in || !out)) return Fail("NULL frame pointer");
   if (nb < 1 || nb > 3) return Fail("num_bands out of range");
   std::vector<Handle*> hs(n);
+  const uint64_t stamp = ++g_call_stamp;
   for (int i = 0; i < n; ++i) {
     Handle* h = AsHandle(hv[i], kMagicF);
     if (!h) return Fail("bad handle in batch");
     if (!h->init_flag) return Fail("handle not initialised");
     if (h->fs != static_cast<Handle*>(hv[0])->fs || h->dev != static_cast<Handle*>(hv[0])->dev)
       return Fail("mixed sample rates or devices in one batch");
+    if (h->seen_stamp == stamp) return Fail("handle listed twice in one batch");
+    h->seen_stamp = stamp;
     hs[i] = h;
   }
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ana)) & 3u)
+    return Fail("float frames must be 4-byte aligned");
+  lk.Device(hs[0]->dev);
   if (frames <= 0) return frames == 0 ? 0 : Fail("negative frame count");
   const uint32_t fs = hs[0]->fs;
   if (fs == 8000 && nb != 1) return Fail("8 kHz has a single band");
@@ -1302,18 +1330,33 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   const size_t per = (size_t)frames * nb * fl, per_a = (size_t)frames * fl;
   if (n > 1 && (in_ss < per || out_ss < per || (ana && ana_ss < per_a))) return Fail("stride shorter than the frames of one stream");
-  const bool split = NeedSplit(hs, ana != nullptr);
+  if (n == 1) {   // one row: the stride is never used to step; a 2-D copy must not see a pitch below its width
+    in_ss = out_ss = per;
+    ana_ss = per_a;
+  }
+  const bool split = NeedSplit(hs, ana != nullptr || phase != 0);
   float *din = nullptr, *dout = nullptr, *dana = nullptr;
-  CU_OK(cudaMalloc(&din, sizeof(float) * per * n));
-  CU_OK(cudaMalloc(&dout, sizeof(float) * per * n));
-  if (ana) CU_OK(cudaMalloc(&dana, sizeof(float) * per_a * n));
+  // single-frame calls on one stream (the reference's own calling pattern) reuse a small per-device scratch
+  const bool small = n == 1 && frames == 1;
+  if (small && !d->d_single) CU_OK(cudaMalloc(&d->d_single, sizeof(float) * (3 * 160 * 2 + 160)));
+  if (small) {
+    din = d->d_single;
+    dout = din + 3 * 160;
+    dana = ana ? dout + 3 * 160 : nullptr;
+  } else {
+    CU_OK(cudaMalloc(&din, sizeof(float) * per * n));
+    CU_OK(cudaMalloc(&dout, sizeof(float) * per * n));
+    if (ana) CU_OK(cudaMalloc(&dana, sizeof(float) * per_a * n));
+  }
   int rc = 0;
   do {
     std::vector<int> slots(n);
     for (int i = 0; i < n; ++i) slots[i] = hs[i]->slot;
     if ((rc = UploadSlots(*d, slots, d->stream)) != 0) break;
-    cudaError_t e = cudaMemcpy2DAsync(din, per * sizeof(float), in, in_ss * sizeof(float), per * sizeof(float), n,
-                                      cudaMemcpyHostToDevice, d->stream);
+    cudaError_t e = cudaSuccess;
+    if (phase != 1)
+      e = cudaMemcpy2DAsync(din, per * sizeof(float), in, in_ss * sizeof(float), per * sizeof(float), n,
+                            cudaMemcpyHostToDevice, d->stream);
     if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
     if (ana) {
       e = cudaMemcpy2DAsync(dana, per_a * sizeof(float), ana, ana_ss * sizeof(float), per_a * sizeof(float), n,
@@ -1335,32 +1378,37 @@ int ProcessBandsF32(void* const* hv, int n, int nb, const float* in, size_t in_s
     p.ana_in = ana ? dana : din;
     p.ana_stream_stride = ana ? (long long)per_a : (long long)per;
     p.ana_frame_stride = ana ? (long long)fl : (long long)nb * fl;
+    p.phase = phase;
     if ((rc = LaunchNsf(fs == 8000 ? 128 : 256, nb, false, split, p, d->stream)) != 0) break;
-    e = cudaMemcpy2DAsync(out, out_ss * sizeof(float), dout, per * sizeof(float), per * sizeof(float), n,
-                          cudaMemcpyDeviceToHost, d->stream);
+    if (phase != 1)
+      e = cudaMemcpy2DAsync(out, out_ss * sizeof(float), dout, per * sizeof(float), per * sizeof(float), n,
+                            cudaMemcpyDeviceToHost, d->stream);
     if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
     e = cudaStreamSynchronize(d->stream);
     if (e != cudaSuccess) { rc = Fail(cudaGetErrorString(e)); break; }
   } while (0);
-  cudaFree(din);
-  cudaFree(dout);
-  if (dana) cudaFree(dana);
+  if (!small) {
+    cudaFree(din);
+    cudaFree(dout);
+    if (dana) cudaFree(dana);
+  }
   return rc;
 }
 
 // Full-band int16 PCM with a separate Analyze signal, host pointers (8/16 kHz, float NS).
 int SplitBatchHost(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
                    int16_t* out, size_t out_stride, int frames) {
-  ApiLock lk;
+  UseLock lk;
   std::vector<Handle*> hs;
   if (!ana) return Fail("NULL Analyze signal");
-  if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (CheckBatch(hv, n, kMagicF, &in_stride, &out_stride, frames, &hs, in, out) != 0) return -1;
   if (frames == 0) return 0;
   const int fl = (int)hs[0]->fs / 100;
   const size_t per = (size_t)frames * fl;
-  if ((ana_stride & 1) || (n > 1 && ana_stride < per)) return Fail("bad Analyze stride");
-  for (int i = 1; i < n; ++i)
-    if (hs[i]->dev != hs[0]->dev) return Fail("split batch spans several GPUs");
+  if ((ana_stride & 1) || (n > 1 && ana_stride < per) || (reinterpret_cast<uintptr_t>(ana) & 3u)) return Fail("bad Analyze stride or alignment");
+  if (n == 1 && ana_stride < per) ana_stride = per;
+  if (t_memo.single_dev < 0) return Fail("split batch spans several GPUs");
+  lk.Device(hs[0]->dev);
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   int16_t* buf = nullptr;
@@ -1382,18 +1430,20 @@ int SplitBatchHost(void* const* hv, int n, const int16_t* ana, size_t ana_stride
 }
 int SplitBatchDevice(void* const* hv, int n, const int16_t* ana, size_t ana_stride, const int16_t* in, size_t in_stride,
                      int16_t* out, size_t out_stride, int frames, void* stream) {
-  ApiLock lk;
+  UseLock lk;
   std::vector<Handle*> hs;
   if (!ana) return Fail("NULL Analyze signal");
-  if (CheckBatch(hv, n, kMagicF, in_stride, out_stride, frames, &hs) != 0) return -1;
+  if (CheckBatch(hv, n, kMagicF, &in_stride, &out_stride, frames, &hs, in, out) != 0) return -1;
   if (frames == 0) return 0;
-  if ((ana_stride & 1) || (n > 1 && ana_stride < (size_t)frames * (hs[0]->fs / 100))) return Fail("bad Analyze stride");
-  for (int i = 1; i < n; ++i)
-    if (hs[i]->dev != hs[0]->dev) return Fail("device batch spans several GPUs");
+  if ((ana_stride & 1) || (n > 1 && ana_stride < (size_t)frames * (hs[0]->fs / 100)) || (reinterpret_cast<uintptr_t>(ana) & 3u))
+    return Fail("bad Analyze stride or alignment");
+  if (t_memo.single_dev < 0) return Fail("device batch spans several GPUs");
+  lk.Device(hs[0]->dev);
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
-  return RunDevice(*d, kMagicF, hs, in, in_stride, out, out_stride, frames, st, nullptr, ana, ana_stride);
+  if (RunDevice(*d, kMagicF, hs, in, in_stride, out, out_stride, frames, st, nullptr, ana, ana_stride) != 0) return -1;
+  return OrderAfterUserStream(*d, st);
 }
 
 // ---- interleaved multi-channel front end (APM_NS::processCaptureStream, libapm/src/apm_ns.cpp:47-132)
@@ -1437,7 +1487,9 @@ __global__ void interleave_kernel(const int16_t* in, T* out, int channels, int s
 // division and classified: equal, one ulp off, worse.  out[0] = hard mismatches (incl. divisions
 // more than one ulp off), out[1] = divisions one ulp off, out[2] = divisions checked, out[3] = nsb_log_rn()
 // results that are not (float)log((double)x) (both are the correctly rounded float except within ~2^-41 /
-// 2^-52 of a rounding boundary: a few per million at most), out[4] = logarithms checked.
+// 2^-52 of a rounding boundary: a few per million at most), out[4] = logarithms checked, out[5] = nsb_exp_rn()
+// results that are not (float)exp((double)x), out[6] = exponentials checked, out[7] = sigmoid maps
+// 0.5f * (nsb_tanh_rn(x) + 1.f) that differ from the one built on the library's tanh (checked as often as out[6]).
 __device__ __forceinline__ void selftest_div(float got, float want, unsigned long long& hard,
                                              unsigned long long& ulp1, unsigned long long& ndiv) {
   ++ndiv;
@@ -1446,7 +1498,7 @@ __device__ __forceinline__ void selftest_div(float got, float want, unsigned lon
   else if (d != 0) ++hard;
 }
 __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned long long* out) {
-  unsigned long long mism = 0, ulp1 = 0, ndiv = 0, lrn = 0, nlog = 0;
+  unsigned long long mism = 0, ulp1 = 0, ndiv = 0, lrn = 0, nlog = 0, ern = 0, nexp = 0, trn = 0;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint32_t h1 = pcm_mix32(seed + (uint32_t)i * 2u + (uint32_t)(i >> 31));
@@ -1485,6 +1537,18 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
         if (d != 0) ++lrn;
         if (d > 1 || d < -1) ++mism;
       }
+      // nsb_exp_rn on [-40, 40] (-logLrt, lquantile, the flatness mean) and beyond both ends of the float range
+      const float xe = ((float)(h1 >> 8) * (1.f / 16777216.f) - 0.5f) * ((h2 & 7u) == 0 ? 260.f : 80.f);
+      {
+        const float got = nsb_exp_rn(xe), want = (float)exp((double)xe);
+        const int d = __float_as_int(got) - __float_as_int(want);
+        ++nexp;
+        if (d != 0) ++ern;
+        if (d > 1 || d < -1) ++mism;
+      }
+      // the sigmoid map of SpeechNoiseProb built on nsb_tanh_rn: arguments from 1e-6 to +-50
+      const float xt = __uint_as_float((h2 & 0x807fffffu) | (((h1 >> 5) % 26u + 107u) << 23));
+      if (__float_as_uint(0.5f * (nsb_tanh_rn(xt) + 1.f)) != __float_as_uint(0.5f * ((float)tanh((double)xt) + 1.f))) ++trn;
     }
     {
       // nsb_sqrtf_p1 == sqrtf + 1 on [0, 2^70): squared spectral magnitudes incl. the tiny end
@@ -1510,6 +1574,9 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
   atomicAdd(out + 2, ndiv);
   if (lrn) atomicAdd(out + 3, lrn);
   atomicAdd(out + 4, nlog);
+  if (ern) atomicAdd(out + 5, ern);
+  atomicAdd(out + 6, nexp);
+  if (trn) atomicAdd(out + 7, trn);
 }
 
 template <typename T>
@@ -1569,14 +1636,15 @@ __global__ void checksum_kernel(const int16_t* pcm, size_t stride, int n_streams
 // (+S16ToFloat) -> D2H, in place (apm_ns.cpp:47-132 does the same per 10 ms on the host).
 template <typename T>
 int ProcessInterleaved(void* const* hv, int channels, T* data, int samples_per_channel) {
-  ApiLock lk;
+  UseLock lk;
   if (!data) return Fail("NULL data");
   std::vector<Handle*> hs;
-  if (CheckBatch(hv, channels, kMagicF, 0, 0, 0, &hs) != 0) return -1;
+  size_t no_stride_in = 0, no_stride_out = 0;
+  if (CheckBatch(hv, channels, kMagicF, &no_stride_in, &no_stride_out, 0, &hs) != 0) return -1;
   const int fl = (int)hs[0]->fs / 100;
   if (samples_per_channel <= 0 || samples_per_channel % fl) return Fail("samples_per_channel must be a multiple of fs/100");
-  for (int i = 1; i < channels; ++i)
-    if (hs[i]->dev != hs[0]->dev) return Fail("channels of one capture stream must share a GPU");
+  if (t_memo.single_dev < 0) return Fail("channels of one capture stream must share a GPU");
+  lk.Device(hs[0]->dev);
   DeviceCtx* d;
   if (DeviceReady(hs[0]->dev, &d) != 0) return -1;
   const int frames = samples_per_channel / fl;
@@ -1650,17 +1718,18 @@ SlabRefs SlabsOf(DeviceCtx& d, const Handle* h, int slot) {
   return r;
 }
 size_t StateSize(const void* hv) {
-  ApiLock lk;
+  UseLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return 0;
   SlabRefs r = SlabsOf(g_devs[h->dev], h, h->slot);
   return sizeof(StateBlobHeader) + r.bytes[0] + r.bytes[1] + r.bytes[2];
 }
 int ExportState(const void* hv, void* buf, size_t size) {
-  ApiLock lk;
+  UseLock lk;
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
   if (!buf) return Fail("NULL buffer");
+  lk.Device(h->dev);
   DeviceCtx* d;
   if (DeviceReady(h->dev, &d) != 0) return -1;
   SlabRefs r = SlabsOf(*d, h, h->slot);
@@ -1689,8 +1758,28 @@ int ExportState(const void* hv, void* buf, size_t size) {
   }
   return 0;
 }
+// What a blob may not carry: the kernels trust the slab's control words.  (The float kernel indexes
+// nothing with them -- its histogram bins are range-checked feature values -- but its counters steer
+// divisions; the fixed-point kernel looks up 1 / (counter + 1) in a 201-entry table.)
+bool BlobHeaderSane(const StateBlobHeader& hd, const char* slab) {
+  if (!(hd.fs == 8000 || hd.fs == 16000 || hd.fs == 32000 || hd.fs == 48000)) return false;
+  if (hd.mode < 0 || hd.mode > 3 || (hd.init_flag != 0 && hd.init_flag != 1)) return false;
+  if (!(hd.down_vsi >= 0.0 && hd.down_vsi < 4096.0)) return false;
+  if (!hd.init_flag) return true;
+  int32_t w[kNsfHdrWords > kNsxHdrWords ? kNsfHdrWords : kNsxHdrWords];
+  memcpy(w, slab, sizeof(w));
+  if (hd.magic == kMagicF) {
+    if (w[kH_blockInd] < -1 || w[kH_updates] < 0 || w[kH_updates] > 200) return false;
+    for (int s = 0; s < 3; ++s)
+      if (w[kH_counter + s] < 0 || w[kH_counter + s] > 200) return false;
+    if (w[kH_modelUpd0] < 0 || w[kH_modelUpd0] > 2 || w[kH_modelUpd3] < 0 || w[kH_modelUpd3] > 500) return false;
+    if ((uint32_t)w[kH_fs] != hd.fs || w[kH_mode] != hd.mode) return false;
+    return true;
+  }
+  return nsx_header_sane(reinterpret_cast<const uint32_t*>(w), hd.fs, hd.mode);
+}
 int ImportState(void* hv, const void* buf, size_t size) {
-  ApiLock lk;
+  ExclusiveLock lk;
   ++g_epoch;   // handle lists validated so far are stale (BatchMemo)
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
@@ -1705,6 +1794,7 @@ int ImportState(void* hv, const void* buf, size_t size) {
   if (hd.state_bytes != r.bytes[0] || hd.hist_bytes != r.bytes[1] || hd.band_bytes != r.bytes[2])
     return Fail("state blob from an incompatible library version");
   if (size < sizeof(hd) + r.bytes[0] + r.bytes[1] + r.bytes[2]) return Fail("state blob truncated");
+  if (!BlobHeaderSane(hd, static_cast<const char*>(buf) + sizeof(hd))) return Fail("state blob carries control words out of range");
   CU_OK(cudaDeviceSynchronize());
   const char* p = static_cast<const char*>(buf) + sizeof(hd);
   for (int k = 0; k < 3; ++k) {
@@ -1723,7 +1813,7 @@ int ImportState(void* hv, const void* buf, size_t size) {
 // Moves a stream to another GPU: new slot there, slabs copied device to device (NVLink peer copy
 // when the GPUs are peers, staged by the driver otherwise), old slot released.
 int MigrateHandle(void* hv, int device) {
-  ApiLock lk;
+  ExclusiveLock lk;
   ++g_epoch;   // handle lists validated so far are stale (BatchMemo)
   Handle* h = AnyHandle(hv);
   if (!h) return Fail("bad handle");
@@ -1766,43 +1856,47 @@ int WebRtcNs_Init(NsHandle* h, uint32_t fs) {
 }
 int WebRtcNs_set_policy(NsHandle* h, int mode) { return SetPolicy(h, mode, kMagicF); }
 
+// WebRtcNs_Analyze updates the statistics itself, as in the reference (ns_core.c:1043-1181): the Analyze half
+// of the frame runs on the GPU at once, so that WebRtcNs_prior_speech_probability read between Analyze and
+// Process (noise_suppression.c:57-66) is current; WebRtcNs_Process then runs the Process half on its own frame
+// (which may differ from the analysed one: audio_processing_impl.cc:625-631).  Process without a preceding
+// Analyze feeds its frame to both halves, as every caller in the reference tree does anyway.
 void WebRtcNs_Analyze(NsHandle* hv, const float* spframe) {
-  ApiLock lk;
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag || !spframe) {
     Fail("WebRtcNs_Analyze: handle not initialised");
     return;
   }
-  memcpy(h->analyze_frame, spframe, sizeof(float) * (h->fs == 8000 ? 80 : 160));
-  h->analyze_seen = true;
+  const int fl = h->fs == 8000 ? 80 : 160;
+  float frame[160];
+  memcpy(frame, spframe, sizeof(float) * fl);
+  void* one = h;
+  if (ProcessBandsF32(&one, 1, 1, nullptr, 0, nullptr, 0, 1, frame, (size_t)fl, 1) == 0) h->analyze_seen = true;
 }
 
 void WebRtcNs_Process(NsHandle* hv, const float* const* spframe, int num_bands, float* const* outframe) {
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag || !spframe || !outframe || num_bands < 1 || num_bands > 3) {
-    ApiLock lk;
     Fail("WebRtcNs_Process: handle not initialised or bad arguments");
     return;
   }
   const int fl = h->fs == 8000 ? 80 : 160;
   float in[3 * 160], out[3 * 160];
   for (int b = 0; b < num_bands; ++b) memcpy(in + b * fl, spframe[b], sizeof(float) * fl);
-  // Analyze recorded its frame; a different band-0 frame here (an echo canceller in between)
-  // takes the split kernel.  Process without a preceding Analyze is fed to both, as every
-  // caller in the reference tree does.
-  const bool distinct = h->analyze_seen && memcmp(h->analyze_frame, in, sizeof(float) * fl) != 0;
+  const bool analysed = h->analyze_seen;
   h->analyze_seen = false;
   void* one = h;
-  if (ProcessBandsF32(&one, 1, num_bands, in, (size_t)num_bands * fl, out, (size_t)num_bands * fl, 1,
-                      distinct ? h->analyze_frame : nullptr, (size_t)fl) != 0)
+  if (ProcessBandsF32(&one, 1, num_bands, in, (size_t)num_bands * fl, out, (size_t)num_bands * fl, 1, nullptr, 0,
+                      analysed ? 2 : 0) != 0)
     return;
   for (int b = 0; b < num_bands; ++b) memcpy(outframe[b], out + b * fl, sizeof(float) * fl);
 }
 
 float WebRtcNs_prior_speech_probability(NsHandle* hv) {
-  ApiLock lk;
+  UseLock lk;
   Handle* h = AsHandle(hv, kMagicF);
   if (!h || !h->init_flag) return -1.f;
+  lk.Device(h->dev);
   DeviceCtx* d;
   if (DeviceReady(h->dev, &d) != 0) return -1.f;
   float v = -1.f;
@@ -1824,11 +1918,11 @@ int WebRtcNsx_set_policy(NsxHandle* h, int mode) { return SetPolicy(h, mode, kMa
 void WebRtcNsx_Process(NsxHandle* hv, const short* const* speechFrame, int num_bands, short* const* outFrame) {
   Handle* h = AsHandle(hv, kMagicX);
   if (!h || !h->init_flag || !speechFrame || !outFrame || num_bands < 1 || num_bands > 3) {
-    ApiLock lk;
     Fail("WebRtcNsx_Process: handle not initialised or bad arguments");
     return;
   }
-  ApiLock lk;
+  UseLock lk;
+  lk.Device(h->dev);
   const int fl = h->fs == 8000 ? 80 : 160;
   const int ana = h->fs == 8000 ? 128 : 256;
   DeviceCtx* d;
@@ -1901,10 +1995,7 @@ int WebRtcNs_AnalyzeProcessBatchDevice(NsHandle* const* hs, int n, const int16_t
 }
 int WebRtcNs_AnalyzeProcessBatchBandsF32(NsHandle* const* hs, int n, int nb, const float* ana, size_t as, const float* in,
                                          size_t is, float* out, size_t os, int frames) {
-  if (!ana) {
-    ApiLock lk;
-    return Fail("NULL Analyze signal");
-  }
+  if (!ana) return Fail("NULL Analyze signal");
   return ProcessBandsF32((void* const*)hs, n, nb, in, is, out, os, frames, ana, as);
 }
 int WebRtcNs_ProcessInterleavedI16(NsHandle* const* hs, int n_channels, int16_t* data, int samples_per_channel) {
@@ -1925,13 +2016,12 @@ int WebRtcNsB200_ExportState(const void* handle, void* buf, size_t size) { retur
 int WebRtcNsB200_ImportState(void* handle, const void* buf, size_t size) { return ImportState(handle, buf, size); }
 int WebRtcNsB200_MigrateHandle(void* handle, int device) { return MigrateHandle(handle, device); }
 int WebRtcNsB200_HandleDevice(const void* handle) {
-  ApiLock lk;
+  UseLock lk;
   Handle* h = AnyHandle(handle);
   return h ? h->dev : -1;
 }
 
-int WebRtcNsB200_SetCreateDevice(int device) {
-  ApiLock lk;
+int WebRtcNsB200_SetCreateDevice(int device) {   // per calling thread
   if (device >= 0) {
     if (EnsureDevices() != 0) return -1;
     if (device >= (int)g_devs.size()) return Fail("bad device index");
@@ -1940,12 +2030,11 @@ int WebRtcNsB200_SetCreateDevice(int device) {
   return 0;
 }
 int WebRtcNsB200_DeviceCount(void) {
-  ApiLock lk;
   if (EnsureDevices() != 0) return 0;
   return (int)g_devs.size();
 }
 int WebRtcNsB200_Synchronize(void) {
-  ApiLock lk;
+  ExclusiveLock lk;
   for (auto& d : g_devs) {
     if (!d.ready) continue;
     CU_OK(cudaSetDevice(d.dev));
@@ -1953,34 +2042,38 @@ int WebRtcNsB200_Synchronize(void) {
   }
   return 0;
 }
-const char* WebRtcNsB200_LastError(void) { return g_err.c_str(); }
+const char* WebRtcNsB200_LastError(void) { return t_err.c_str(); }   // of the calling thread
 uint64_t WebRtcNsB200_KernelLaunches(void) { return g_launches; }
 
 int WebRtcNsB200_SelfTestStats(uint64_t n_cases, uint64_t* stats) {
-  ApiLock lk;
+  UseLock lk;
   int dev = 0;
   if (EnsureDevices() != 0) return -1;
   cudaGetDevice(&dev);
+  lk.Device(dev);
   DeviceCtx* d;
   if (DeviceReady(dev, &d) != 0) return -1;
   unsigned long long* bad = nullptr;
-  CU_OK(cudaMalloc(&bad, 5 * sizeof(*bad)));
-  CU_OK(cudaMemsetAsync(bad, 0, 5 * sizeof(*bad), d->stream));
+  CU_OK(cudaMalloc(&bad, 8 * sizeof(*bad)));
+  CU_OK(cudaMemsetAsync(bad, 0, 8 * sizeof(*bad), d->stream));
   selftest_kernel<<<148 * 4, 256, 0, d->stream>>>(n_cases, 12345u, bad);
   ++g_launches;
-  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CU_OK(cudaMemcpyAsync(h, bad, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
   CU_OK(cudaStreamSynchronize(d->stream));
   cudaFree(bad);
-  for (int i = 0; i < 5; ++i) stats[i] = h[i];
+  for (int i = 0; i < 8; ++i) stats[i] = h[i];
   return 0;
 }
 int WebRtcNsB200_SelfTest(uint64_t n_cases) {
-  uint64_t st[5] = {0, 0, 0, 0, 0};
+  uint64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (WebRtcNsB200_SelfTestStats(n_cases, st) != 0) return -1;
   if (st[0] != 0) return Fail("self-test: " + std::to_string(st[0]) + " arithmetic mismatches");
   if (st[3] * 100000ull > st[4])
     return Fail("self-test: " + std::to_string(st[3]) + " of " + std::to_string(st[4]) + " logarithms not the rounded double-precision one");
+  if (st[5] * 100000ull > st[6] || st[7] * 100000ull > st[6])
+    return Fail("self-test: " + std::to_string(st[5]) + " exponentials / " + std::to_string(st[7]) + " sigmoid maps of " +
+                std::to_string(st[6]) + " not the rounded double-precision ones");
   // fdiv(): correctly rounded except for a handful of near-halfway quotients (ns_warp.cuh)
   if (st[1] * 1000000ull > st[2] * 2ull)
     return Fail("self-test: " + std::to_string(st[1]) + " of " + std::to_string(st[2]) + " divisions one ulp off");
@@ -1989,7 +2082,6 @@ int WebRtcNsB200_SelfTest(uint64_t n_cases) {
 
 int WebRtcNsB200_SynthPcmDevice(int16_t* dst, size_t stride, int n_streams, uint32_t first_stream, uint32_t fs,
                                 uint32_t first_sample, uint32_t n_samples, uint32_t seed, void* st) {
-  ApiLock lk;
   if ((stride & 1) || (n_samples & 1)) return Fail("stride and n_samples must be even");
   if (n_streams <= 0 || n_samples == 0) return 0;
   unsigned gx = (n_samples / 2 + 255) / 256;
@@ -2007,7 +2099,6 @@ void WebRtcNsB200_SynthPcmHost(int16_t* dst, uint32_t stream, uint32_t fs, uint3
 }
 int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
                                 int64_t* sums, void* st) {
-  ApiLock lk;
   checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 0);
   ++g_launches;
   CU_OK(cudaGetLastError());
@@ -2015,7 +2106,6 @@ int WebRtcNsB200_ChecksumDevice(const int16_t* pcm, size_t stride, int n_streams
 }
 int WebRtcNsB200_ChecksumAccumulateDevice(const int16_t* pcm, size_t stride, int n_streams, uint32_t n_samples,
                                           int64_t* sums, void* st) {
-  ApiLock lk;
   checksum_kernel<<<n_streams, 256, 0, (cudaStream_t)st>>>(pcm, stride, n_streams, n_samples, (long long*)sums, 1);
   ++g_launches;
   CU_OK(cudaGetLastError());

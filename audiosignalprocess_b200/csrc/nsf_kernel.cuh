@@ -370,8 +370,12 @@ nsf_process_kernel(const NsfLaunch p) {
     }
   };
   // the first frame's PCM goes out with the state copies, before anything is waited for
-  if (live && p.frames > 0) load_frame(0, cur);
-  if (SPLIT && live && p.frames > 0) load_ana(0, curA);
+  // p.phase (split kernels only): 1 = the Analyze half of every frame alone, 2 = the Process half alone -- the
+  // single-stream WebRtcNs_Analyze / WebRtcNs_Process pair, whose statistics must be current in between
+  // (WebRtcNs_prior_speech_probability, noise_suppression.c:57-66); 0 = both.
+  const bool doA = !SPLIT || p.phase != 2, doP = !SPLIT || p.phase != 1;
+  if (doP && live && p.frames > 0) load_frame(0, cur);
+  if (SPLIT && doA && live && p.frames > 0) load_ana(0, curA);
 
   mbar_wait_cta(barT, 0);
   if (!live) return;  // whole warp leaves; no block barriers below
@@ -420,20 +424,22 @@ nsf_process_kernel(const NsfLaunch p) {
       for (int u = 0; u < 2; ++u)
         if (lane + 32 * u < G::kHP) t[u] = blkA[G::kFP + lane + 32 * u];
       __syncwarp();
+      if (doA) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (lane + 32 * u < G::kHP) blkA[lane + 32 * u] = t[u];
+        for (int u = 0; u < 2; ++u)
+          if (lane + 32 * u < G::kHP) blkA[lane + 32 * u] = t[u];
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (lane + 32 * u < G::kFP) blkA[G::kHP + lane + 32 * u] = pcm_unpack(SPLIT ? curA[u] : cur[0][u]);
+        for (int u = 0; u < kU; ++u)
+          if (lane + 32 * u < G::kFP) blkA[G::kHP + lane + 32 * u] = pcm_unpack(SPLIT ? curA[u] : cur[0][u]);
+      }
       __syncwarp();
       // The next frame's loads are issued only now, after this frame's words were consumed: the
       // consumer waits on a scoreboard shared by every load this static instruction has in
       // flight, so issuing the prefetch first made it wait for the prefetch itself (10 % of the
       // kernel's stall samples sat on the int16 unpack above).
       if (f + 1 < p.frames) {
-        load_frame(f + 1, nxt);
-        if (SPLIT) load_ana(f + 1, nxtA);
+        if (doP) load_frame(f + 1, nxt);
+        if (SPLIT && doA) load_ana(f + 1, nxtA);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = lane < G::kL ? blkA[lane + G::kL * j] : make_float2(0.f, 0.f);
@@ -454,7 +460,7 @@ nsf_process_kernel(const NsfLaunch p) {
     // one vote, and the five dependent shuffle + add steps of the sum itself (needed only by the
     // gain compensation much later) are issued next to the FFT, where there is independent work to
     // hide them behind.  The reductions are a tenth of this kernel's stall samples.
-    const bool nzA = __any_sync(kFullMask, energy1 != 0.f);
+    const bool nzA = doA && __any_sync(kFullMask, energy1 != 0.f);
     bool nzP = nzA;   // the same frame on the Process side unless SPLIT
 
     float2 o0[kU];  // band-0 output pairs
@@ -532,17 +538,9 @@ nsf_process_kernel(const NsfLaunch p) {
         }
       }
       // ---- pass A: signalEnergy, sumMagn, sum of lmagn, sum of magnAvgPause, each summed bin after bin as the
-      // reference sums them (chain_sum4: four lanes, one chain each).  A 129-step dependent chain; it sits in
-      // one basic block with the tracker updates of (d), which need none of its results.
-      float sigE, sumMagn, sumLog, sumPause;
-      {
-        const float c = chain_sum4<G::kStg, G::kStg>(stg, lane);
-        sigE = __shfl_sync(kFullMask, c, 0);
-        sumMagn = __shfl_sync(kFullMask, c, 1);
-        sumLog = __shfl_sync(kFullMask, c, 2);
-        sumPause = __shfl_sync(kFullMask, c, 3);
-      }
-      const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
+      // reference sums them (ChainSum4: four lanes, one chain each).  A 129-step dependent chain: it advances
+      // between the tracker updates of (d), which need none of its results.
+      ChainSum4<G::kStg, G::kStg> chainA(stg, lane);
 
       // ---- (d) NoiseEstimation (ns_core.c:217-285)
       int updates = HIr[kH_updates];
@@ -583,6 +581,7 @@ nsf_process_kernel(const NsfLaunch p) {
           lq[s] = up ? lq[s] + step : lq[s] - step;
           if (fabsf(lmagn[j] - lq[s]) < 0.01f)
             dn[s] = fdiv_r(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s], rc1[s]);
+          chainA.advance(2);
         }
         noise[j] = quant;
         if (!nyq || lane == 0) {
@@ -591,6 +590,15 @@ nsf_process_kernel(const NsfLaunch p) {
           *reinterpret_cast<float4*>(R + 4) = make_float4(dn[1], dn[2], quant, r1.w);
         }
       }
+      float sigE, sumMagn, sumLog, sumPause;
+      {
+        const float c = chainA.finish();
+        sigE = __shfl_sync(kFullMask, c, 0);
+        sumMagn = __shfl_sync(kFullMask, c, 1);
+        sumLog = __shfl_sync(kFullMask, c, 2);
+        sumPause = __shfl_sync(kFullMask, c, 3);
+      }
+      const float signalEnergy = NSB_FDIV_C(sigE, kMagnLenF);
       // latch (every frame during start-up, then once per tracker period) outside the slot loop,
       // so that the 15 tracker updates above form one block the scheduler can interleave
       if (sel >= 0) {
@@ -706,10 +714,18 @@ nsf_process_kernel(const NsfLaunch p) {
         }
       }
       __syncwarp();
-      // ---- pass B: covMagnPause, varPause, varMagn, sum of logLrtTimeAvg, bin after bin
+      // ---- pass B: covMagnPause, varPause, varMagn, sum of logLrtTimeAvg, bin after bin -- advancing between the
+      // exponentials of SpeechNoiseProb's last loop (ns_core.c:743-747), which need no feature: (float)exp(-logLrt)
       float cov, varP, varM, lsum;
+      float invLrt[G::kSlots];
       {
-        const float c = chain_sum4<G::kStg, G::kStg>(stg, lane);
+        ChainSum4<G::kStg, G::kStg> chainB(stg, lane);
+#pragma unroll
+        for (int j = 0; j < G::kSlots; ++j) {
+          invLrt[j] = nsb_exp_rn(-logLrt[j]);
+          chainB.advance(7);
+        }
+        const float c = chainB.finish();
         cov = __shfl_sync(kFullMask, c, 0);
         varP = __shfl_sync(kFullMask, c, 1);
         varM = __shfl_sync(kFullMask, c, 2);
@@ -800,8 +816,7 @@ nsf_process_kernel(const NsfLaunch p) {
         const float gainPrior = fdiv(1.f - prior, prior + 0.0001f);
 #pragma unroll
         for (int j = 0; j < G::kSlots; ++j) {
-          float inv = nsb_exp_rn(-logLrt[j]);   // (float)exp(-logLrtTimeAvg[i]): ns_core.c:744
-          inv = gainPrior * inv;
+          const float inv = gainPrior * invLrt[j];
           prob[j] = fdiv(1.f, 1.f + inv);
         }
       }
@@ -852,7 +867,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
     }
 
-    if (SPLIT) {
+    if (SPLIT && doP) {
       // ======== WebRtcNs_ProcessCore front end on its own signal (ns_core.c:1225-1267)
       blockInd = HIw[kH_blockInd];
       {
@@ -923,6 +938,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
     }
 
+    if (doP) {
     if (!nzP) {
       // ---- zero input to Process (ns_core.c:1239-1264): flush the overlap, high bands pass
       // through the delay line ungained.
@@ -938,8 +954,6 @@ nsf_process_kernel(const NsfLaunch p) {
     } else {
       // ======== WebRtcNs_ProcessCore from the Wiener filter on
       // ---- (k) Wiener filter, flooring, start-up blend (ns_core.c:985-1007, 1268-1307)
-      float hbProbSum = 0.f, hbGainSum = 0.f;
-      float sumMagnA = 0.f, sumMagnP = 0.f;   // split mode, high bands (ns_core.c:1376-1382)
       float gainW[G::kSlots];
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
@@ -984,7 +998,10 @@ nsf_process_kernel(const NsfLaunch p) {
           R[kB_smooth] = flt;
           if (SPLIT) {
             // ns_core.c:1309-1310: magnPrevProcess = magn, noisePrev = noise
-            if (NB > 1) { sumMagnA += R[kB_magnPrev]; sumMagnP += magn[j]; }
+            if (NB > 1) {   // terms of sumMagnAnalyze / sumMagnProcess (:1372-1377), summed in bin order below
+              stg[2 * G::kStg + k] = R[kB_magnPrev];
+              stg[3 * G::kStg + k] = magn[j];
+            }
             R[kB_noisePrev] = noise[j];
             X_magnP[k] = magn[j];
           } else {
@@ -993,11 +1010,13 @@ nsf_process_kernel(const NsfLaunch p) {
           scr[k] = z;
         }
         if (NB > 1) {
-          // averages over the top quarter of the band, bins [magnLen - d - 1, magnLen - 1)
+          // averages over the top quarter of the band, bins [magnLen - d - 1, magnLen - 1): one slot of all 32
+          // lanes; its terms go to the staging arrays and are summed in bin order in (n)
           constexpr int d = G::kBins / 4;
-          if (!nyq && k >= G::kBins - d - 1 && k < G::kBins - 1) {
-            hbProbSum += prob[j];
-            hbGainSum += flt;
+          static_assert(NB == 1 || (d == 32 && (G::kBins - d - 1) % 32 == 0), "the high-band averages cover one slot");
+          if (j == (G::kBins - d - 1) / 32) {
+            stg[lane] = prob[j];
+            stg[G::kStg + lane] = flt;
           }
         }
       }
@@ -1086,16 +1105,23 @@ nsf_process_kernel(const NsfLaunch p) {
       // ---- (n) high-band time-domain gain (ns_core.c:1362-1404)
       if (NB > 1) {
         constexpr int d = G::kBins / 4;
-        warp_sum2(hbProbSum, hbGainSum);
+        float hbProbSum, hbGainSum;
+        {
+          ChainSum4<32, G::kStg> ch(stg, lane);   // (staged in (k); a __syncwarp lies in between)
+          const float c = ch.finish();
+          hbProbSum = __shfl_sync(kFullMask, c, 0);
+          hbGainSum = __shfl_sync(kFullMask, c, 1);
+        }
         float avgProb = hbProbSum / (float)d;
         // sumMagnProcess / sumMagnAnalyze == 1 when Analyze and Process see one frame
         if (SPLIT) {
-          warp_sum2(sumMagnA, sumMagnP);
-          avgProb *= sumMagnP / sumMagnA;
+          ChainSum4<G::kStg, G::kStg> ch(stg, lane);
+          const float c = ch.finish();
+          avgProb *= __shfl_sync(kFullMask, c, 3) / __shfl_sync(kFullMask, c, 2);
         }
         const float avgGain = hbGainSum / (float)d;
         const float tmp = 2.f * avgProb - 1.f;
-        const float gmod = 0.5f * (1.f + tanhf(tmp));
+        const float gmod = 0.5f * (1.f + nsb_tanh_rn(tmp));
         float g = 0.5f * gmod + 0.5f * avgGain;
         if (avgProb >= 0.5f) g = 0.25f * gmod + 0.75f * avgGain;
         if (g < denoiseBound) g = denoiseBound;
@@ -1140,6 +1166,7 @@ nsf_process_kernel(const NsfLaunch p) {
       }
       __syncwarp();
     }
+    }   // doP
 
 #pragma unroll
     for (int b = 0; b < NB; ++b)

@@ -90,6 +90,7 @@ struct NsfLaunch {
   long long out_stream_stride, out_frame_stride, out_band_stride;
   int n_streams;
   int frames;
+  int phase = 0;           // split kernels: 1 = Analyze half only, 2 = Process half only, 0 = both (nsf_kernel.cuh)
 };
 
 }  // namespace nsb200

@@ -135,6 +135,20 @@ inline void nsx_init_state(uint32_t* slab, uint32_t fs) {
   nsx_set_mode(slab, 0);
 }
 
+// Control words of a state slab that arrives from outside (WebRtcNsB200_ImportState): the kernel indexes the
+// 1 / (counter + 1) table with the counters and shifts by the Q-domain words.
+inline bool nsx_header_sane(const uint32_t* slab, uint32_t fs, int mode) {
+  const int32_t* w = reinterpret_cast<const int32_t*>(slab);
+  if (w[kX_blockIndex] < -1) return false;
+  for (int s = 0; s < 3; ++s)
+    if (w[kX_counter + s] < 0 || w[kX_counter + s] > 200) return false;
+  if (w[kX_cntThresUpdate] < 0 || w[kX_cntThresUpdate] > 500) return false;
+  const int q[4] = {w[kX_minNorm], w[kX_qNoise], w[kX_prevQNoise], w[kX_prevQMagn]};
+  for (int k = 0; k < 4; ++k)
+    if (q[k] < -64 || q[k] > 64) return false;
+  return (uint32_t)w[kX_fs] == fs && w[kX_mode] == mode;
+}
+
 }  // namespace nsb200
 
 #endif  // AUDIOSIGNALPROCESS_B200_NSX_HOST_INIT_H_

@@ -40,33 +40,120 @@ def algorithmic_bytes(kind, fs, frames_per_launch):
     return io + 2.0 * S_HOT[(kind, fs)] / frames_per_launch
 
 
-def measured_traffic(kernel, frames_per_launch, streams):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu summary of the SAME
-    configuration (profiles/r1_*.json), else None."""
+def _profile_summary(kernel, frames_per_launch, streams):
+    """The committed ncu summary (profiles/r<round>_*.json, newest round first) of the SAME kernel and
+    configuration, with its file name; (None, None) if there is none."""
     tag = {"nsf_process_kernel": "nsf", "nsx_process_kernel": "nsx"}.get(kernel)
-    for name in ("r1_%s_kernel_F%d.json" % (tag, frames_per_launch),
-                 "r1_%s_kernel_F%d_%d.json" % (tag, frames_per_launch, streams)):
-        try:
-            d = json.load(open(os.path.join(ROOT, "profiles", name)))
-            if d["units_per_launch"] == streams * frames_per_launch:
-                return d["dram_bytes_per_launch"]
-        except Exception:
-            pass
-    return None
+    for rnd in ("r2", "r1"):
+        for name in ("%s_%s_kernel_F%d.json" % (rnd, tag, frames_per_launch),
+                     "%s_%s_kernel_F%d_%d.json" % (rnd, tag, frames_per_launch, streams)):
+            try:
+                d = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if d["units_per_launch"] == streams * frames_per_launch:
+                    return d, "profiles/" + name
+            except Exception:
+                pass
+    return None, None
+
+
+def measured_traffic(kernel, frames_per_launch, streams):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary of the same configuration."""
+    d, _ = _profile_summary(kernel, frames_per_launch, streams)
+    return d["dram_bytes_per_launch"] if d else None
 
 
 def measured_instructions(kernel, frames_per_launch, streams):
     """Warp instructions per stream-frame of the dominant kernel from the committed ncu summary of the
-    same configuration, else None (for the issue-rate view of a kernel that is not HBM-bound)."""
-    tag = {"nsf_process_kernel": "nsf", "nsx_process_kernel": "nsx"}.get(kernel)
-    path = os.path.join(ROOT, "profiles", "r1_%s_kernel_F%d.json" % (tag, frames_per_launch))
-    try:
-        d = json.load(open(path))
-        if d["units_per_launch"] == streams * frames_per_launch:
-            return d["warp_instructions_per_unit"]
-    except Exception:
-        pass
-    return None
+    same configuration (for the issue-rate view of a kernel that is not HBM-bound)."""
+    d, _ = _profile_summary(kernel, frames_per_launch, streams)
+    return d["warp_instructions_per_unit"] if d else None
+
+
+def pcie_probe(torch, dev, mbytes=128, reps=6):
+    """Host<->device copy ceiling of THIS rank's GPU as the end-to-end path uses it: pinned buffers, an H2D
+    and a D2H copy in flight together on two streams.  Returns GB/s per direction (both directions move
+    `mbytes` per repetition at once)."""
+    n = mbytes * 1000 * 1000 // 2
+    h_in = torch.empty(n, dtype=torch.int16).pin_memory()
+    h_out = torch.empty(n, dtype=torch.int16).pin_memory()
+    d_a = torch.empty(n, dtype=torch.int16, device=dev)
+    d_b = torch.empty(n, dtype=torch.int16, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return n * 2 / best / 1e9
+
+
+def extra_leg(pkg, lib, torch, dev, stream, kind, fs, streams, F, mode, steps=10, warmup=3):
+    """One more configuration of BASELINE.json's list on this GPU, device-resident like `value`: timed with
+    CUDA events over `steps` launches, its HBM roofline, and a parity flag from sampled streams checked
+    against the compiled reference (oracle/_ref) on the first F frames."""
+    import numpy as np
+    fl = fs // 100
+    fixed = kind == "fixed"
+    total = (warmup + steps) * F * fl
+    pcm_in = torch.empty((streams, total), dtype=torch.int16, device=dev)
+    pcm_out = torch.empty_like(pcm_in)
+    rc = lib.WebRtcNsB200_SynthPcmDevice(C.c_void_p(pcm_in.data_ptr()), total, streams, 0, fs, 0, total, 1234,
+                                         C.c_void_p(stream.cuda_stream))
+    assert rc == 0, lib.WebRtcNsB200_LastError()
+    batch = pkg.NsBatch(streams, fs, mode, fixed=fixed, devices=[dev.index])
+
+    def step(i):
+        off = i * F * fl * 2
+        batch.process_device(pcm_in.data_ptr() + off, total, pcm_out.data_ptr() + off, total, F, stream.cuda_stream)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        step(warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # parity: sampled streams, the first F frames (fresh state), against the unmodified reference
+    parity = "unchecked (oracle/_ref missing)"
+    ref = ref_lib()
+    if ref is not None:
+        sample = sorted({0, 1, 2, 3, streams // 2, streams - 1})
+        idx = torch.tensor(sample, dtype=torch.long, device=dev)
+        xin = pcm_in[idx, :F * fl].cpu().numpy()
+        got = pcm_out[idx, :F * fl].cpu().numpy()
+        worst = 0
+        for k in range(len(sample)):
+            want = np.zeros(F * fl, np.int16)
+            x1 = np.ascontiguousarray(xin[k])
+            if fixed:
+                ref.ref_nsx_run(fs, mode, F, x1.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p))
+            else:
+                ref.ref_ns_run(fs, mode, F, x1.ctypes.data_as(C.c_void_p), None, want.ctypes.data_as(C.c_void_p), None)
+            worst = max(worst, int(np.abs(got[k].astype(np.int32) - want.astype(np.int32)).max()))
+        tol = 0 if fixed else (1 if fs <= 16000 else 4)
+        parity = ("bit-exact" if worst == 0 else "max |diff| %d LSB" % worst) + " on %d sampled streams x %d frames vs the reference%s" % (
+            len(sample), F, "" if worst <= tol else " -- OUT OF TOLERANCE")
+    batch.close()
+    del pcm_in, pcm_out
+    torch.cuda.empty_cache()
+    peak, which = measured_peak_gbs()
+    bsf = algorithmic_bytes(kind, fs, F)
+    achieved = bsf * streams * F / (ms * 1e-3) / 1e9
+    return {"workload": "%d streams x %d Hz, %s policy %d, F=%d frames per launch" % (
+                streams, fs, "WebRtcNsx fixed" if fixed else "WebRtcNs float", mode, F),
+            "value": streams * F * 0.01 / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "bytes_per_stream_frame": bsf, "peak_source": which},
+            "parity": parity}
 
 
 def measured_peak_gbs():
@@ -335,6 +422,7 @@ def main():
     ap.add_argument("--no-tick", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the NSx 16/8 kHz x 8192 and 48 kHz x 2048 legs of the N=1 line")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -478,10 +566,25 @@ def main():
 
         v_block = timed(run_blocking)
         v_stream = timed(run_streaming)
+        # what the copies could do at best: every rank probes its own GPU's H2D + D2H duplex rate at the same
+        # time (ranks share the host's memory / PCIe fabric); the end-to-end path moves bytes_per_step each way
+        barrier()
+        probe = pcie_probe(torch, dev)
+        pt = torch.tensor([probe], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+        probe_total = float(pt.item())
+        bytes_dir = a.streams * n1 * 2
+        gbs_dir = v_stream / (a.streams * F * 0.01 * world) * bytes_dir * world / 1e9   # steps/s x bytes per step, all ranks
         e2e = {"value": v_stream, "unit": "audio-s/s",
-               "h2d_bytes_per_step": a.streams * n1 * 2, "d2h_bytes_per_step": a.streams * n1 * 2,
+               "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
                "api": "WebRtcNs%s_ProcessBatchAsync + WebRtcNsB200_WaitBatch, two steps in flight" % ("x" if a.fixed else ""),
-               "blocking_value": v_block, "blocking_api": "WebRtcNs%s_ProcessBatch, one call per step" % ("x" if a.fixed else "")}
+               "blocking_value": v_block, "blocking_api": "WebRtcNs%s_ProcessBatch, one call per step" % ("x" if a.fixed else ""),
+               "pcie_gbs": gbs_dir, "pcie_probe_gbs": probe_total,
+               "pcie_note": "GB/s per direction summed over the %d rank(s), both directions busy at once: what the end-to-end "
+                            "leg moved, and what a bare pinned-buffer H2D + D2H copy pair per rank reaches on this box at "
+                            "the same time" % world,
+               "frac_of_pcie_probe": gbs_dir / probe_total if probe_total > 0 else None}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -494,6 +597,7 @@ def main():
         kname = "nsx_process_kernel" if a.fixed else "nsf_process_kernel"
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": measured_traffic(kname, F, a.streams) if a.fs == 16000 else None,
+                    "traffic_source": _profile_summary(kname, F, a.streams)[1] if a.fs == 16000 else None,
                     "peak_source": which, "kernel": kname,
                     "bytes_per_stream_frame": bytes_per_sf, "frames_per_launch": F,
                     "launch_ms_avg": avg_ms, "launch_ms_median": med}
@@ -503,7 +607,7 @@ def main():
         clk = sampler.summary().get("sm_mhz")
         if wi and clk:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            roofline["issue"] = {"warp_instructions_per_stream_frame": wi, "source": "ncu summary under profiles/",
+            roofline["issue"] = {"warp_instructions_per_stream_frame": wi, "source": _profile_summary(kname, F, a.streams)[1],
                                  "frac_of_issue_peak": wi * a.streams * F / (avg_ms * 1e-3) / (4.0 * sms * clk * 1e6)}
         cpu = None
         if not a.no_cpu:
@@ -517,15 +621,21 @@ def main():
                        "sample": "%d streams x %d frames per step, %d timed steps after %d warm-up steps on persistent handles, "
                                  "%d pthreads taking one stream at a time" % (a.streams, F, done, a.warmup, cores)}
         tick = None
+        extra = None
         if world == 1 and not a.no_tick and F != 1:
             del pcm_in, pcm_out
             torch.cuda.empty_cache()
             tick = tick_roofline(a, pkg, lib, torch, dev, stream, kind)
+        if world == 1 and not a.no_extra and not a.fixed and a.fs == 16000 and F == 100:
+            # BASELINE.json configs[2] and configs[3] beside the headline (configs[1]), so that the driver's record holds them
+            extra = {"nsx_16k_8192": extra_leg(pkg, lib, torch, dev, stream, "fixed", 16000, 8192, 100, a.mode),
+                     "nsx_8k_8192": extra_leg(pkg, lib, torch, dev, stream, "fixed", 8000, 8192, 100, a.mode),
+                     "float_48k_2048": extra_leg(pkg, lib, torch, dev, stream, "float", 48000, 2048, 50, a.mode)}
         line = {"metric": "ns_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32" if a.fixed else "f32",
                 "data": "synthetic", "config": config, "clocks": sampler.summary(), "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_tick": tick, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_tick": tick, "extra": extra, "cpu_baseline": cpu}
         print(json.dumps(line))
     batch.close()
     if world > 1:

@@ -167,9 +167,10 @@ uint64_t WebRtcNsB200_KernelLaunches(void);
  * n_cases operands: logf, sqrtf, int16 rounding and the floor square root must be identical;
  * the branch-free division must equal IEEE division except for at most 2 per million quotients
  * that may be one ulp off; the tracker's logarithm must be the double-precision logarithm rounded
- * to float (never more than an ulp off, at most 1 in 100 000 not identical).  stats[5]: [0] hard
- * mismatches, [1] divisions one ulp off, [2] divisions checked, [3] logarithms not identical,
- * [4] logarithms checked.  0 = pass. */
+ * to float, likewise the exponential and the sigmoid map built on tanh (never more than an ulp off, at
+ * most 1 in 100 000 not identical).  stats[8]: [0] hard mismatches, [1] divisions one ulp off,
+ * [2] divisions checked, [3] logarithms not identical, [4] logarithms checked, [5] exponentials not
+ * identical, [6] exponentials checked, [7] sigmoid maps not identical (of [6]).  0 = pass. */
 int WebRtcNsB200_SelfTest(uint64_t n_cases);
 int WebRtcNsB200_SelfTestStats(uint64_t n_cases, uint64_t* stats);
 /* Deterministic synthetic PCM (csrc/pcm_synth.h) written on the device:

@@ -36,6 +36,9 @@ int nsx_oracle_run(int fs, int mode, int nframes, const int16_t* pcm_in, int16_t
 int nsx_oracle_real_fft(int order, int inverse, const int16_t* in, int16_t* out);
 const int16_t* nsx_oracle_table(const char* name, int* len);
 
+/* the float path's real FFT alone (n = 256 / 128; isgn >= 0 forward, < 0 backward unscaled), in place */
+int nsf_oracle_rdft(int n, int isgn, float* a);
+
 /* ---- 32/48 kHz band split / merge (AudioBuffer + SplittingFilter) ---- */
 typedef struct BandOracle BandOracle;
 BandOracle* band_oracle_create(int fs);

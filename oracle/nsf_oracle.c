@@ -356,6 +356,21 @@ static void rdft_backward(const NsfOracle* s, float* a) {
   }
 }
 
+/* test hook: the transform alone (n = 256 or 128; isgn >= 0 forward, < 0 backward, unscaled), pinned
+ * bit for bit against WebRtc_rdft in tests/test_oracle_pinning.py */
+int nsf_oracle_rdft(int n, int isgn, float* a) {
+  NsfOracle* s;
+  if (n != 256 && n != 128) return -1;
+  s = nsf_oracle_create();
+  if (!s) return -1;
+  s->ana = n;
+  fft_tables(s);
+  if (isgn >= 0) rdft_forward(s, a);
+  else rdft_backward(s, a);
+  nsf_oracle_free(s);
+  return 0;
+}
+
 /* FFT() of ns_core.c:886-911 */
 static void rfft_fwd(const NsfOracle* s, float* x, float* xr, float* xi) {
   const int h = s->ana / 2;

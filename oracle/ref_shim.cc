@@ -427,6 +427,31 @@ int ref_ns_trace(int fs, int mode, int nframes, const int16_t* pcm_in, float* ou
   return 0;
 }
 
+// Float NS frame by frame with WebRtcNs_prior_speech_probability read BETWEEN Analyze and Process
+// (noise_suppression.c:57-66; 8/16 kHz).  prior_mid: one value per frame.
+int ref_ns_prior_between(int fs, int mode, int nframes, const int16_t* pcm_in, float* out_f32, float* prior_mid) {
+  if (!(fs == 8000 || fs == 16000)) return -1;
+  NsHandle* h = NULL;
+  if (WebRtcNs_Create(&h) != 0) return -1;
+  if (WebRtcNs_Init(h, (uint32_t)fs) != 0 || WebRtcNs_set_policy(h, mode) != 0) {
+    WebRtcNs_Free(h);
+    return -1;
+  }
+  const int n = FrameLen(fs);
+  std::vector<float> in(n), out(n);
+  for (int f = 0; f < nframes; ++f) {
+    for (int i = 0; i < n; ++i) in[i] = (float)pcm_in[(size_t)f * n + i];
+    const float* inb[1] = {in.data()};
+    float* outb[1] = {out.data()};
+    WebRtcNs_Analyze(h, in.data());
+    prior_mid[f] = WebRtcNs_prior_speech_probability(h);
+    WebRtcNs_Process(h, inb, 1, outb);
+    memcpy(out_f32 + (size_t)f * n, out.data(), sizeof(float) * n);
+  }
+  WebRtcNs_Free(h);
+  return 0;
+}
+
 // The reference's real FFT itself (utility/fft4g.c:324) with fresh work arrays, as ns_core.c:886-944 calls it.
 void ref_rdft(int n, int isgn, float* a) {
   std::vector<int> ip(2 + 64, 0);        // IP_LENGTH of ns_core.h covers n <= 256

@@ -104,18 +104,25 @@ def snr_db(ref, out):
 
 
 # ---- float parity criteria ---------------------------------------------------------------
-# STRICT is BASELINE.json's tolerance.  The float algorithm branches on knife-edge comparisons
-# (|lmagn - lquantile| < WIDTH, speechProb > PROB_RANGE, ...), so two conforming builds of the
-# REFERENCE ITSELF (plain vs FMA-contracted, oracle/Makefile) leave each other by up to ~170 LSB /
-# 65 dB on some of our streams; any float implementation that is not bit-identical to one
-# particular build shows the same kind of rare branch flips.  Hence two gates:
-#   strict   -- max abs <= 1e-4 FS and SNR >= 90 dB: required for most streams of every case,
-#   envelope -- SNR >= 55 dB and max abs <= 1e-2 FS: required for every stream; this is the
-#               deviation the reference shows against itself (test_reference_self_consistency).
+# STRICT is BASELINE.json's tolerance: per stream max abs <= 1e-4 full scale and SNR of the difference
+# >= 90 dB.  Every GPU float test requires it of EVERY stream (min_strict_frac = 1.0), and the tests of the
+# float-sample interfaces additionally hold the kernel to what it actually delivers (FLOAT_MAX_ABS /
+# FLOAT_MIN_SNR below; measured on the B200 over 256 streams x 60 s at 8 and 16 kHz: worst 0.027 LSB,
+# 133.9 dB -- profiles/r2_float_parity.md).
+# Why that is reachable: the float algorithm branches on comparisons decided by the last bit of its
+# operands (|lmagn - lquantile| < WIDTH, lmagn > lquantile, speechProb > PROB_RANGE, histogram bins), so
+# two conforming builds of the REFERENCE ITSELF (plain vs FMA-contracted, oracle/Makefile) leave each
+# other by hundreds of LSB on most 60 s streams (test_reference_sensitivity.py).  The kernel therefore
+# keeps the whole decision-directed recursion bit-identical to the plain build (test_gpu_float_exact_state.py);
+# only the synthesis (inverse FFT, window, overlap-add) rounds differently.
+#   envelope -- SNR >= 55 dB and max abs <= 1e-2 FS: what two builds of the reference show against each
+#               other; kept as the outer gate (a failure there is a bug, not a rounding).
 STRICT_MAX_ABS = 1e-4 * 32768.0
 STRICT_MIN_SNR = 90.0
 ENVELOPE_MAX_ABS = 1e-2 * 32768.0
 ENVELOPE_MIN_SNR = 55.0
+FLOAT_MAX_ABS = 0.25     # LSB, float-sample outputs at 8/16 kHz
+FLOAT_MIN_SNR = 120.0    # dB
 
 
 def judge_float(ref, out, slack=0.0):
@@ -130,8 +137,10 @@ def judge_float(ref, out, slack=0.0):
     return strict, env, err, snr
 
 
-def summarize_parity(results, what, min_strict_frac):
-    """results: list of judge_float tuples. Asserts the two gates, returns a printable line."""
+def summarize_parity(results, what, min_strict_frac=1.0, max_abs=None, min_snr=None):
+    """results: list of judge_float tuples.  Asserts the gates (strict for at least min_strict_frac of the
+    streams -- 1.0 everywhere on the GPU --, envelope for all, and optionally a tighter max abs [LSB] /
+    min SNR [dB] for every stream); returns the printable line."""
     n = len(results)
     n_strict = sum(1 for r in results if r[0])
     worst_err = max(r[2] for r in results)
@@ -141,6 +150,10 @@ def summarize_parity(results, what, min_strict_frac):
     print(line)
     assert all(r[1] for r in results), "outside the reference's own cross-build envelope: " + line
     assert n_strict >= min_strict_frac * n, "too few streams within the strict tolerance: " + line
+    if max_abs is not None:
+        assert worst_err <= max_abs, "max abs above %.3f LSB: %s" % (max_abs, line)
+    if min_snr is not None:
+        assert worst_snr >= min_snr, "SNR below %.1f dB: %s" % (min_snr, line)
     return line
 
 

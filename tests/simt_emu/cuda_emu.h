@@ -31,6 +31,7 @@
 #define __launch_bounds__(...)
 #define __shared__
 #define NSB_DEV static inline
+#define NSB_DEVM inline
 
 namespace simt_emu {
 

@@ -90,8 +90,11 @@ int emu_nsf_state_words(void) { return kNsfStateWords; }
 // Split mode (float samples): Analyze sees ana[stream][frame][fl], Process sees in[stream][frame][band][fl].
 // The first `fused_frames` frames run through the fused kernel on `in` (ana ignored) so that the
 // fused -> split hand-over of a running stream is exercised.
-int emu_nsf_run_split(int fs, int mode, int nb, int nstreams, int nframes, int fpl, int fused_frames,
-                      const float* ana_in, const float* in, float* out) {
+// phased != 0: every launch of the split kernel is issued as two, the Analyze half then the Process half (the
+// single-stream WebRtcNs_Analyze / WebRtcNs_Process pair); prior_mid (optional, [stream][frame], fpl == 1):
+// the prior speech probability in the state between the two.
+int emu_nsf_run_split_phased(int fs, int mode, int nb, int nstreams, int nframes, int fpl, int fused_frames,
+                             const float* ana_in, const float* in, float* out, int phased, float* prior_mid) {
   const int ana = fs == 8000 ? 128 : 256;
   const int fl = fs == 8000 ? 80 : 160;
   Fn fs_fn = PickSplit(ana, nb), ff_fn = Pick(ana, nb, false);
@@ -125,10 +128,25 @@ int emu_nsf_run_split(int fs, int mode, int nb, int nstreams, int nframes, int f
     p.ana_frame_stride = fl;
     p.n_streams = nstreams;
     p.frames = nf;
-    simt_emu::launch(fused ? ff_fn : fs_fn, &p, (nstreams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta, kNsfWarpsPerCta * 32);
+    const int grid = (nstreams + kNsfWarpsPerCta - 1) / kNsfWarpsPerCta;
+    if (fused || !phased) {
+      simt_emu::launch(fused ? ff_fn : fs_fn, &p, grid, kNsfWarpsPerCta * 32);
+    } else {
+      p.phase = 1;
+      simt_emu::launch(fs_fn, &p, grid, kNsfWarpsPerCta * 32);
+      if (prior_mid && fpl == 1)
+        for (int s = 0; s < nstreams; ++s)
+          prior_mid[(size_t)s * nframes + f0] = ((float*)&state[(size_t)s * kNsfStateWords])[kH_priorSpeechProb];
+      p.phase = 2;
+      simt_emu::launch(fs_fn, &p, grid, kNsfWarpsPerCta * 32);
+    }
     f0 += nf;
   }
   return 0;
+}
+int emu_nsf_run_split(int fs, int mode, int nb, int nstreams, int nframes, int fpl, int fused_frames,
+                      const float* ana_in, const float* in, float* out) {
+  return emu_nsf_run_split_phased(fs, mode, nb, nstreams, nframes, fpl, fused_frames, ana_in, in, out, 0, NULL);
 }
 
 void emu_nsf_tables(float* win256, float* win128) {

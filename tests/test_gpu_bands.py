@@ -41,7 +41,7 @@ def test_float_multiband_parity(nslib, reflib, fs, mode):
     for s in range(n):
         _, refi, pp = reflib.ns(fs, mode, x[s])
         res.append(judge_float(refi, out[s], slack=1.0))
-    summarize_parity(res, "float multi-band fs=%d mode=%d" % (fs, mode), 0.6)
+    summarize_parity(res, "float multi-band fs=%d mode=%d" % (fs, mode), 1.0)
     b.close()
 
 

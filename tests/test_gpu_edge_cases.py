@@ -199,3 +199,88 @@ def test_computed_and_listed_slots_agree(nslib, fixed):
     b.close()
     assert ref.any()
     assert np.array_equal(ref, out)
+
+
+def test_batch_validation_rejects_what_the_kernels_cannot_take(nslib):
+    """Misaligned PCM pointers (the kernels move 32-bit words), a handle listed twice (two warps on one
+    slab) and -- accepted -- a single stream whose stride is shorter than its frames (never used to step)."""
+    lib = nslib.load_library()
+    fs, frames = 16000, 10
+    b = nslib.NsBatch(2, fs, 2, fixed=True)
+    buf = np.zeros(2 * frames * 160 + 8, np.int16)
+    out = np.zeros_like(buf)
+    base, obase = buf.ctypes.data, out.ctypes.data
+    assert lib.WebRtcNsx_ProcessBatch(b._handles, 2, C.c_void_p(base + 2), frames * 160, C.c_void_p(obase), frames * 160, frames) == -1
+    assert b"aligned" in lib.WebRtcNsB200_LastError()
+    assert lib.WebRtcNsx_ProcessBatch(b._handles, 2, C.c_void_p(base), frames * 160, C.c_void_p(obase + 2), frames * 160, frames) == -1
+    twice = (C.c_void_p * 2)(b._handles[0], b._handles[0])
+    assert lib.WebRtcNsx_ProcessBatch(twice, 2, C.c_void_p(base), frames * 160, C.c_void_p(obase), frames * 160, frames) == -1
+    assert b"twice" in lib.WebRtcNsB200_LastError()
+    one = (C.c_void_p * 1)(b._handles[1])
+    x = nslib.synth_pcm_host(1, fs, frames * 160)
+    o1 = np.zeros_like(x)
+    assert lib.WebRtcNsx_ProcessBatch(one, 1, C.c_void_p(x.ctypes.data), 0, C.c_void_p(o1.ctypes.data), 2, frames) == 0, \
+        lib.WebRtcNsB200_LastError()
+    b2 = nslib.NsBatch(1, fs, 2, fixed=True)
+    assert np.array_equal(o1, b2.process(x))
+    b.close()
+    b2.close()
+
+
+def test_calls_from_several_threads(nslib, reflib):
+    """Independent handles driven from independent host threads (the reference keeps no shared state,
+    ns/noise_suppression.c:20-66): four threads, each with its own batch and its own create/process/free
+    cycle, all at once on one device; and the last error is the calling thread's own."""
+    import threading
+    lib = nslib.load_library()
+    fs, mode, frames, n = 16000, 2, 120, 6
+    xs = [nslib.synth_pcm_host(n, fs, frames * 160, base_seed=100 + t) for t in range(4)]
+    outs, errs = [None] * 4, [None] * 4
+
+    def work(t):
+        try:
+            b = nslib.NsBatch(n, fs, mode, fixed=True)
+            o = np.zeros_like(xs[t])
+            for f0 in range(0, frames, 15):
+                o[:, f0 * 160:(f0 + 15) * 160] = b.process(np.ascontiguousarray(xs[t][:, f0 * 160:(f0 + 15) * 160]))
+            outs[t] = o
+            if t == 1:   # provoke an error in this thread only
+                assert lib.WebRtcNsx_ProcessBatch(b._handles, n, None, 1, None, 1, 1) == -1
+                errs[t] = lib.WebRtcNsB200_LastError()
+            else:
+                errs[t] = b""
+            b.close()
+        except Exception as e:   # noqa: BLE001
+            errs[t] = repr(e).encode()
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert errs[1] == b"strides must be even", errs
+    assert errs[0] == b"" and errs[2] == b"" and errs[3] == b"", errs
+    for t in range(4):
+        for s in (0, n - 1):
+            assert np.array_equal(outs[t][s], reflib.nsx(fs, mode, xs[t][s]))
+
+
+def test_device_call_on_a_user_stream_is_ordered_before_later_library_calls(nslib, reflib):
+    """A launch enqueued on the caller's stream by a *Device entry point, immediately followed by calls that
+    use the library's own stream (the getter, a host-pointer batch, Free): no synchronisation by the caller."""
+    import torch
+    lib = nslib.load_library()
+    fs, mode, n, frames = 16000, 2, 64, 300
+    x = nslib.synth_pcm_host(n, fs, 2 * frames * 160)
+    st = torch.cuda.Stream()
+    d_in = torch.from_numpy(x[:, :frames * 160].copy()).cuda()
+    d_out = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+    b = nslib.NsBatch(n, fs, mode, fixed=True)
+    b.process_device(d_in.data_ptr(), frames * 160, d_out.data_ptr(), frames * 160, frames, st.cuda_stream)
+    second = b.process(np.ascontiguousarray(x[:, frames * 160:]))     # library stream, right behind it
+    b.close()                                                          # Free right behind that
+    torch.cuda.synchronize()
+    first = d_out.cpu().numpy()
+    for s in (0, 31, n - 1):
+        assert np.array_equal(np.concatenate([first[s], second[s]]), reflib.nsx(fs, mode, x[s]))

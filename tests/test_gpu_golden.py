@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import judge_float, summarize_parity
+from conftest import FLOAT_MAX_ABS, FLOAT_MIN_SNR, judge_float, summarize_parity
 from test_golden import FILES, load
 
 pytestmark = pytest.mark.gpu
@@ -23,5 +23,5 @@ def test_gpu_reproduces_golden(path, nslib):
     for i in range(n):
         if res[i][0]:
             assert abs(bf.prior_speech_probability(i) - float(g["ns_prior_prob"][i][-1])) <= 5e-4
-    summarize_parity(res, "float GPU vs golden %s" % os.path.basename(path), 0.6)
+    summarize_parity(res, "float GPU vs golden %s" % os.path.basename(path), 1.0, max_abs=FLOAT_MAX_ABS, min_snr=FLOAT_MIN_SNR)
     bf.close()

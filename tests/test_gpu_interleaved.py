@@ -64,4 +64,4 @@ def test_interleaved_matches_apm_ns(nslib, reflib, fs, channels, as_float):
     scale = 32768.0 if as_float else 1.0
     res = [judge_float(ref[c::channels].astype(np.float64) * scale, out[c::channels].astype(np.float64) * scale,
                        slack=1.0) for c in range(channels)]
-    summarize_parity(res, "interleaved fs=%d ch=%d float=%s" % (fs, channels, as_float), 0.5)
+    summarize_parity(res, "interleaved fs=%d ch=%d float=%s" % (fs, channels, as_float), 1.0)

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import judge_float, summarize_parity
+from conftest import FLOAT_MAX_ABS, FLOAT_MIN_SNR, judge_float, summarize_parity
 from test_emulated_kernels import split_signals
 
 pytestmark = pytest.mark.gpu
@@ -59,7 +59,7 @@ def test_band_frame_entry(nslib, reflib, fs, mode, nb, fused):
     for s in range(n):
         ref = reflib.ns_split(fs, mode, ana[s], x[s], nb, fused)
         res.append(judge_float(ref.ravel(), out[s].ravel()))
-    summarize_parity(res, "split bands fs=%d nb=%d" % (fs, nb), 0.6)
+    summarize_parity(res, "split bands fs=%d nb=%d" % (fs, nb), 1.0, max_abs=FLOAT_MAX_ABS, min_snr=FLOAT_MIN_SNR)
     _free(lib, hs)
     assert per > 0
 
@@ -100,7 +100,7 @@ def test_int16_pcm_entries(nslib, reflib, device_ptrs):
         ref = reflib.ns_split(fs, mode, ana[s].astype(np.float32), x[s].astype(np.float32).reshape(frames, 1, fl), 1, 0)
         refi = np.clip(np.where(ref > 0, np.floor(ref + 0.5), np.ceil(ref - 0.5)), -32768, 32767).ravel()
         res.append(judge_float(refi, out[s].astype(np.float32), slack=1.0))
-    summarize_parity(res, "split int16 pcm", 0.6)
+    summarize_parity(res, "split int16 pcm", 1.0, max_abs=1.0)
     _free(lib, hs)
 
 

@@ -81,6 +81,15 @@ def test_import_rejects_wrong_kind_and_garbage(nslib):
     junk = (C.c_ubyte * size)()
     assert lib.WebRtcNsB200_ImportState(f[0], junk, size) == -1           # no tag
     assert lib.WebRtcNsB200_ExportState(f[0], buf, 16) == -1              # buffer too small
+    # control words out of range: fs, a tracker counter (header 696 bytes, then the slab: counters at words 2-4)
+    bad = (C.c_ubyte * size).from_buffer_copy(bytes(buf))
+    bad[8:12] = (44100).to_bytes(4, "little")
+    assert lib.WebRtcNsB200_ImportState(f[0], bad, size) == -1
+    bad = (C.c_ubyte * size).from_buffer_copy(bytes(buf))
+    bad[696 + 8:696 + 12] = (100000).to_bytes(4, "little")
+    assert lib.WebRtcNsB200_ImportState(f[0], bad, size) == -1
+    assert b"out of range" in lib.WebRtcNsB200_LastError()
+    assert lib.WebRtcNsB200_ImportState(f[0], buf, size) == 0             # the untouched blob still goes in
     assert lib.WebRtcNsB200_StateSize(None) == 0
     lib.WebRtcNs_Free(f[0])
     lib.WebRtcNsx_Free(xh[0])
