@@ -119,7 +119,7 @@ struct DeviceCtx {
   int pipe_count = 0;                  //   streams per buffer
   unsigned long long pipe_seq = 0;     // chunks issued so far (buffer = seq % 3)
   // 32/48 kHz: one CUDA stream per pipeline stage, events between the stages of a chunk
-  cudaStream_t stage_stream[9] = {};
+  cudaStream_t stage_stream[9] = {}, stage_stream_hi[9] = {};   // per pipeline position; _hi: the QMF stages
   cudaEvent_t fork_event = nullptr;
   std::vector<cudaEvent_t> band_events;
 };
@@ -838,7 +838,16 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
   const int nstages = band_stages + (host ? 2 : 0);
   if (!d.fork_event) {
     CU_OK(cudaEventCreateWithFlags(&d.fork_event, cudaEventDisableTiming));
-    for (int k = 0; k < kBandMaxStages; ++k) CU_OK(cudaStreamCreateWithFlags(&d.stage_stream[k], cudaStreamNonBlocking));
+    // The QMF stages are serial recurrences on a few dozen warps: the pipeline's critical path.  Their streams
+    // get the highest priority, so that a chunk's QMF blocks take the next free SM slot ahead of the queued
+    // blocks of the wide stages (resamplers, suppressor) of other chunks.
+    int prio_lo = 0, prio_hi = 0;
+    CU_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("NSB200_BAND_NOPRIO")) prio_hi = prio_lo;
+    for (int k = 0; k < kBandMaxStages; ++k) {
+      CU_OK(cudaStreamCreateWithPriority(&d.stage_stream[k], cudaStreamNonBlocking, prio_lo));
+      CU_OK(cudaStreamCreateWithPriority(&d.stage_stream_hi[k], cudaStreamNonBlocking, prio_hi));
+    }
   }
   while (d.band_events.size() < (size_t)nstages * nchunks) {
     cudaEvent_t e;
@@ -859,14 +868,19 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
   // every stage stream starts after the caller's stream: inputs are ready and the previous
   // block has released the scratch
   CU_OK(cudaEventRecord(d.fork_event, st));
-  for (int k = 0; k < nstages; ++k) CU_OK(cudaStreamWaitEvent(d.stage_stream[k], d.fork_event, 0));
-  mark(d.stage_stream[0]);
+  auto stage_of = [&](int k) -> cudaStream_t {
+    const int bk = k - first;   // band stage index: QMF stages are 1, 2, 4, 5 of 7 (48 kHz) or 0, 2 of 3 (32 kHz)
+    const bool qmf = bk >= 0 && bk < band_stages && bk != ns_stage && !(nb == 3 && (bk == 0 || bk == 6));
+    return qmf ? d.stage_stream_hi[k] : d.stage_stream[k];
+  };
+  for (int k = 0; k < nstages; ++k) CU_OK(cudaStreamWaitEvent(stage_of(k), d.fork_event, 0));
+  mark(stage_of(0));
   const int ana = 256;
   for (int c = 0; c < nchunks; ++c) {
     const int f0 = c * chunk;
     const int nf = frames - f0 < chunk ? frames - f0 : chunk;
     for (int k = 0; k < nstages; ++k) {
-      cudaStream_t s = d.stage_stream[k];
+      cudaStream_t s = stage_of(k);
       if (k > 0) CU_OK(cudaStreamWaitEvent(s, d.band_events[(size_t)c * nstages + k - 1], 0));
       const int bk = k - first;   // band stage index
       if (bk < 0) {

@@ -44,81 +44,96 @@ NSB_DEV unsigned fx_sqrt_floor(unsigned v) {
 }
 
 // ---- warp-wide int16 complex FFT -------------------------------------------
-// N = 256 (8 stages) or 128 (7 stages) complex points, LANES = N/8 active lanes,
-// 8 points per lane as packed words (re in the low half, im in the high half).
-// Radix-2 decimation in time in exactly the reference's stage order; three
-// register layouts, two conflict-free shared-memory transposes:
+// N = 256 (8 stages) or 128 (7 stages) complex points, LANES = N/8 active lanes, 8 points per lane.
+// Radix-2 decimation in time in exactly the reference's stage order (complex_fft.c:29-158 forward, :160-301
+// inverse, mode 1) with its truncating int16 store after every stage; three register layouts, two
+// conflict-free shared-memory transposes:
 //   A: position p = 8*lane + r                      stages 0,1,2
 //   B: p = (lane&7) + 8*r + 64*(lane>>3)            stages 3,4,5
 //   C: p = lane + LANES*r                           stages 6(,7)
-// tw[t] = (cos, sin)(2*pi*t/256) = (kSinTable1024[4t+256], kSinTable1024[4t]) packed.
+// The points stay UNPACKED in registers between the stages of a layout (re[8], im[8] as sign-extended
+// ints): the reference's `(int16_t)(x >> 15)` is bits 15..30 of x, i.e. the upper half of 2x, so with every
+// term of the butterfly doubled the truncating store is one arithmetic shift by 16, and nothing is packed or
+// unpacked around a stage (16 instructions per forward butterfly where the packed form took ~40).  Words
+// are packed (re low, im high) only to cross a transpose.
+//
+// Twiddles (cos, sin)(2 pi t / 256) = (kSinTable1024[4t + 256], kSinTable1024[4t]) arrive as int2 in a table
+// regrouped per stage so that the lanes of a warp read consecutive entries (the butterflies of stage s use
+// t = (p mod 2^s) << (7 - s): strided, up to 8-way bank conflicts straight from a linear table):
+//   [0, 4)            stages 0-2: t = 32 q
+//   [4 + 8 g, ..+8)   stages 3-5, g = 0 (s=3) | 1 + (r&1) (s=4) | 3 + (r&3) (s=5): t for lane&7 = 0..7
+//   [60, 124)         stage 6: N=256: (r&1)*32 + lane;  N=128: (r&3)*16 + lane
+//   [124, 252)        stage 7 (N=256): (r&3)*32 + lane = t itself
+constexpr int kFxTwInt2 = 252;   // filled on the host: nsx_host_init.h nsx_fill_fft_twiddles
+
 NSB_DEV int fx_swz(int p) { return p ^ ((p >> 3) & 7) ^ (((p >> 6) & 3) << 3); }
 
 NSB_DEV uint32_t fx_pack(int re, int im) { return ((uint32_t)re & 0xffffu) | ((uint32_t)im << 16); }
 NSB_DEV int fx_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 NSB_DEV int fx_hi(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
-// One butterfly of complex_fft.c mode 1. INV=false: forward (wi = -sin, fixed
-// shift 1); INV=true: inverse (wi = +sin, `shift` in 0..2, round2 = 8192 << shift).
+// One butterfly on unpacked points a (kept) and x (twiddled), w = (cos, sin).
+// Forward: t = ((wr xr + ws xi + 1) >> 1, (wr xi - ws xr + 1) >> 1); out = (int16)((a 2^14 -+ t + 2^14) >> 15).
+// Inverse: t = ((wr xr - ws xi + 1) >> 1, (wr xi + ws xr + 1) >> 1); out = (int16)((a 2^14 -+ t + (2^13 << shift)) >> (14 + shift)).
+// Both as the upper half of the 32-bit sum scaled to put the kept bits at 16..31 (wrap-around included: the
+// discarded top bits are the ones the int16 cast discards).
 template <bool INV>
-NSB_DEV void fx_butterfly(uint32_t& lo_w, uint32_t& hi_w, uint32_t tw, int shift) {
-  const int wr = fx_lo(tw), ws = fx_hi(tw);
-  const int xr = fx_lo(hi_w), xi = fx_hi(hi_w);
-  int tr, ti;
+NSB_DEV void fx_butterfly_u(int& ar, int& ai, int& xr, int& xi, int2 w, int shift) {
+  unsigned tr, ti;
   if (INV) {
-    tr = (wr * xr - ws * xi + 1) >> 1;
-    ti = (wr * xi + ws * xr + 1) >> 1;
+    const int pr = w.x * xr - w.y * xi + 1, pi = w.x * xi + w.y * xr + 1;
+    tr = (unsigned)(pr >> 1) << (2 - shift);
+    ti = (unsigned)(pi >> 1) << (2 - shift);
   } else {
-    tr = (wr * xr + ws * xi + 1) >> 1;
-    ti = (wr * xi - ws * xr + 1) >> 1;
+    const int pr = w.x * xr + w.y * xi + 1, pi = w.x * xi - w.y * xr + 1;
+    tr = (unsigned)pr & ~1u;
+    ti = (unsigned)pi & ~1u;
   }
-  const int qr = fx_lo(lo_w) * 16384, qi = fx_hi(lo_w) * 16384;
-  const int rnd = INV ? (8192 << shift) : 16384;
-  const int sh = INV ? (shift + 14) : 15;
-  hi_w = fx_pack((qr - tr + rnd) >> sh, (qi - ti + rnd) >> sh);
-  lo_w = fx_pack((qr + tr + rnd) >> sh, (qi + ti + rnd) >> sh);
+  const unsigned qr = ((unsigned)ar << (INV ? 16 - shift : 15)) + 32768u;
+  const unsigned qi = ((unsigned)ai << (INV ? 16 - shift : 15)) + 32768u;
+  xr = (int)(qr - tr) >> 16;
+  xi = (int)(qi - ti) >> 16;
+  ar = (int)(qr + tr) >> 16;
+  ai = (int)(qi + ti) >> 16;
 }
 
-// max |int16| over the 8 packed words of this lane (no 32768 clamp yet)
-NSB_DEV int fx_lane_max_abs(const uint32_t (&v)[8]) {
-  int m = 0;
+// The inverse transform's scaling decision before a stage (complex_fft.c:186-198): the largest |value| of all
+// 2N int16 (32768 counts as 32767) against 13573 and 27146.
+NSB_DEV int fx_inverse_shift(const int (&re)[8], const int (&im)[8], bool act) {
+  int mx = 0, mn = 0;
+  if (act) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    int a = fx_lo(v[r]), b = fx_hi(v[r]);
-    a = a < 0 ? -a : a;
-    b = b < 0 ? -b : b;
-    m = a > m ? a : m;
-    m = b > m ? b : m;
+    for (int r = 0; r < 8; ++r) {
+      mx = re[r] > mx ? re[r] : mx;
+      mx = im[r] > mx ? im[r] : mx;
+      mn = re[r] < mn ? re[r] : mn;
+      mn = im[r] < mn ? im[r] : mn;
+    }
   }
-  return m;
+  int m = -mn > mx ? -mn : mx;
+  m = warp_max_i(m);
+  return (m > 13573 ? 1 : 0) + (m > 27146 ? 1 : 0);   // (32768 vs 32767: both above either threshold)
 }
 
-// Runs the stages whose butterfly span lies inside the lane (local bits
-// bit0..bit0+nbits-1 of r), for first stage index s0.  pos(r) gives the global
-// position of local element r.  Returns the accumulated inverse scale.
-template <bool INV, int N, int S0, int NST, int BIT0, typename PosFn>
-NSB_DEV int fx_local_stages(uint32_t (&v)[8], const uint32_t* tw, bool act, PosFn pos) {
+// Runs NST stages starting at stage S0 on the lane's 8 points; the butterfly partners differ in local bit
+// BIT0 + t.  twi(s, r) = index of the butterfly's twiddle in the regrouped table.  Returns the accumulated
+// inverse scale.
+template <bool INV, int S0, int NST, int BIT0, typename TwFn>
+NSB_DEV int fx_local_stages_u(int (&re)[8], int (&im)[8], const int2* tw, bool act, TwFn twi) {
   int scale = 0;
 #pragma unroll
   for (int t = 0; t < NST; ++t) {
-    const int s = S0 + t;          // stage: span l = 2^s
     int shift = 0;
     if (INV) {
-      // complex_fft.c:186-198: scan all 2N values before every stage
-      int m = act ? fx_lane_max_abs(v) : 0;
-      m = warp_max_i(m);
-      if (m > 32767) m = 32767;
-      if (m > 13573) ++shift;
-      if (m > 27146) ++shift;
+      shift = fx_inverse_shift(re, im, act);
       scale += shift;
     }
     if (act) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (!((r >> (BIT0 + t)) & 1)) {
-          const int p = pos(r);
-          const int tix = (p & ((1 << s) - 1)) << (7 - s);
-          fx_butterfly<INV>(v[r], v[r | (1 << (BIT0 + t))], tw[tix], shift);
+          const int r2 = r | (1 << (BIT0 + t));
+          fx_butterfly_u<INV>(re[r], im[r], re[r2], im[r2], tw[twi(S0 + t, r)], shift);
         }
       }
     }
@@ -126,41 +141,53 @@ NSB_DEV int fx_local_stages(uint32_t (&v)[8], const uint32_t* tw, bool act, PosF
   return scale;
 }
 
-// Full transform. in: layout A (v[r] = element at position 8*lane + r, already
-// in bit-reversed order, i.e. position p holds sample bitrev(p)).
-// out: layout C (v[r] = element lane + LANES*r). scr: N words of scratch.
+// Full transform. in: layout A (re/im[r] = point at position 8*lane + r, already in bit-reversed order, i.e.
+// position p holds sample bitrev(p)).  out: layout C (point lane + LANES*r).  scr: N words of scratch.
 template <bool INV, int N>
-NSB_DEV int fx_warp_cfft(uint32_t (&v)[8], uint32_t* scr, const uint32_t* tw, int lane) {
+NSB_DEV int fx_warp_cfft(int (&re)[8], int (&im)[8], uint32_t* scr, const int2* tw, int lane) {
   constexpr int LANES = N / 8;
   constexpr int STAGES = N == 256 ? 8 : 7;
   const bool act = lane < LANES;
+  const int l7 = lane & 7;
   int scale = 0;
-  scale += fx_local_stages<INV, N, 0, 3, 0>(v, tw, act, [&](int r) { return 8 * lane + r; });
+  // stages 0-2: t = (r mod 2^s) << (7 - s) = 32 * {0 | 2 (r&1) | r&3}
+  scale += fx_local_stages_u<INV, 0, 3, 0>(re, im, tw, act, [&](int s, int r) { return s == 0 ? 0 : (s == 1 ? 2 * (r & 1) : (r & 3)); });
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) scr[fx_swz(8 * lane + r)] = v[r];
+    for (int r = 0; r < 8; ++r) scr[fx_swz(8 * lane + r)] = fx_pack(re[r], im[r]);
   }
   __syncwarp();
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = scr[fx_swz((lane & 7) + 8 * r + 64 * (lane >> 3))];
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t w = scr[fx_swz(l7 + 8 * r + 64 * (lane >> 3))];
+      re[r] = fx_lo(w);
+      im[r] = fx_hi(w);
+    }
   }
   __syncwarp();
-  scale += fx_local_stages<INV, N, 3, 3, 0>(v, tw, act,
-                                           [&](int r) { return (lane & 7) + 8 * r + 64 * (lane >> 3); });
+  // stages 3-5: the butterfly's position mod 2^s is l7 + 8 (r mod 2^(s-3))
+  scale += fx_local_stages_u<INV, 3, 3, 0>(re, im, tw, act, [&](int s, int r) {
+    return 4 + 8 * (s == 3 ? 0 : (s == 4 ? 1 + (r & 1) : 3 + (r & 3))) + l7;
+  });
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) scr[fx_swz((lane & 7) + 8 * r + 64 * (lane >> 3))] = v[r];
+    for (int r = 0; r < 8; ++r) scr[fx_swz(l7 + 8 * r + 64 * (lane >> 3))] = fx_pack(re[r], im[r]);
   }
   __syncwarp();
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = scr[fx_swz(lane + LANES * r)];
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t w = scr[fx_swz(lane + LANES * r)];
+      re[r] = fx_lo(w);
+      im[r] = fx_hi(w);
+    }
   }
   __syncwarp();
   // remaining stages 6..STAGES-1 act on the top local bits of layout C
-  scale += fx_local_stages<INV, N, 6, STAGES - 6, (N == 256 ? 1 : 2)>(
-      v, tw, act, [&](int r) { return lane + LANES * r; });
+  scale += fx_local_stages_u<INV, 6, STAGES - 6, (N == 256 ? 1 : 2)>(re, im, tw, act, [&](int s, int r) {
+    return s == 6 ? 60 + (N == 256 ? (r & 1) * 32 : (r & 3) * 16) + lane : 124 + (r & 3) * 32 + lane;
+  });
   return scale;
 }
 

@@ -27,6 +27,29 @@ namespace nsb200 {
 
 inline int nsx_rnd(double x) { return (int)floor(x + 0.5); }
 
+// FFT twiddles as (cos, sin) int pairs regrouped per stage (layout in ns_fixed.cuh, "Twiddles"): tw[t] is the
+// packed 256-point table, n the transform length (256 / 128 complex points).
+inline void nsx_fill_fft_twiddles(const uint32_t* tw, int n, int32_t* out) {
+  auto put = [&](int idx, int t) {
+    out[2 * idx] = (int32_t)(int16_t)(tw[t] & 0xffffu);
+    out[2 * idx + 1] = (int32_t)(int16_t)(tw[t] >> 16);
+  };
+  for (int q = 0; q < 4; ++q) put(q, 32 * q);                                   // stages 0-2
+  for (int l = 0; l < 8; ++l) {                                                 // stages 3-5
+    put(4 + l, l << 4);
+    for (int b = 0; b < 2; ++b) put(4 + 8 * (1 + b) + l, (l + 8 * b) << 3);
+    for (int b = 0; b < 4; ++b) put(4 + 8 * (3 + b) + l, (l + 8 * b) << 2);
+  }
+  if (n == 256) {
+    for (int b = 0; b < 2; ++b)
+      for (int l = 0; l < 32; ++l) put(60 + b * 32 + l, (l + 32 * b) << 1);     // stage 6
+    for (int t = 0; t < 128; ++t) put(124 + t, t);                              // stage 7
+  } else {
+    for (int b = 0; b < 4; ++b)
+      for (int l = 0; l < 16; ++l) put(60 + b * 16 + l, (l + 16 * b) << 1);     // stage 6
+  }
+}
+
 inline void nsx_fill_tables(NsxTables* t) {
   memset(t, 0, sizeof(*t));
   const double pi = 3.14159265358979323846;
@@ -95,6 +118,7 @@ inline void nsx_fill_tables(NsxTables* t) {
     memcpy(img, v == 0 ? (const void*)t->win256 : (const void*)t->win128, v == 0 ? sizeof(t->win256) : sizeof(t->win128));
     memcpy(img + 128, t->tw, sizeof(t->tw));
     memcpy(img + 256, t->log_frac, sizeof(t->log_frac));
+    nsx_fill_fft_twiddles(t->tw, v == 0 ? 256 : 128, reinterpret_cast<int32_t*>(img + kNsxImgFftTw));
   }
 }
 

@@ -34,7 +34,10 @@ namespace nsb200 {
 // as many lock-stepped warps per CTA as possible: one 28-warp CTA per SM at 4096 streams
 // (measured 4.07 -> 2.99 ms per 4096 x 100 frames; more barriers per frame were slower).
 constexpr int kNsxWarpsPerCta = 2;        // smallest CTA (and the emulator's)
-constexpr int kNsxMaxWarpsPerCta = 28;    // 72 registers x 896 threads, 168 KB of shared memory
+#ifndef NSX_MAX_WARPS
+#define NSX_MAX_WARPS 28
+#endif
+constexpr int kNsxMaxWarpsPerCta = NSX_MAX_WARPS;    // 72 registers x 896 threads, 168 KB of shared memory
 #ifndef NSX_FRAME_SYNC
 #define NSX_FRAME_SYNC 1
 #endif
@@ -203,7 +206,7 @@ nsx_process_kernel(const NsxLaunch p) {
   extern __shared__ uint4 nsx_smem4[];
   uint32_t* smem = reinterpret_cast<uint32_t*>(nsx_smem4);
   int16_t* s_win = reinterpret_cast<int16_t*>(smem);
-  uint32_t* s_tw = smem + 128;
+  const int2* s_tw = reinterpret_cast<const int2*>(smem + kNsxImgFftTw);   // FFT twiddles, regrouped per stage
   int16_t* s_logf = reinterpret_cast<int16_t*>(smem + 256);
 
   const int lane = lane_id();
@@ -388,7 +391,7 @@ nsx_process_kernel(const NsxLaunch p) {
       const int q_magn = norm_data - STAGES;
 
       // ---- forward FFT: NormalizeRealBuffer (:543) -> bit reversal -> radix-2 stages
-      uint32_t v[8];
+      int vr[8], vi[8];
       {
         // position 8*lane + r holds sample bitrev(8*lane + r) = rev5(lane) + LANES*rev3(r):
         // the samples of lane rev(lane), in order rev3(r)
@@ -397,32 +400,32 @@ nsx_process_kernel(const NsxLaunch p) {
         for (int r = 0; r < 8; ++r) {
           const int rr = ((r & 1) << 2) | (r & 2) | ((r >> 2) & 1);
           const int nv = fx_s16(fx_shl(wd[rr], norm_data));
-          const int got = __shfl_sync(kFullMask, nv, src_lane & 31);
-          v[r] = fx_pack(got, 0);
+          vr[r] = __shfl_sync(kFullMask, nv, src_lane & 31);
+          vi[r] = 0;
         }
       }
-      fx_warp_cfft<false, ANA>(v, scr, s_tw, lane);
+      fx_warp_cfft<false, ANA>(vr, vi, scr, s_tw, lane);
 
       // ---- spectrum, magnitude (nsx_core.c:1247-1272)
       int re[NSLOT], im[NSLOT];
       unsigned magn[NSLOT];
-      const uint32_t nyq_w = __shfl_sync(kFullMask, v[4], 0);  // position HALF sits in lane 0, r = 4
+      const int nyq_re = __shfl_sync(kFullMask, vr[4], 0);  // position HALF sits in lane 0, r = 4
       unsigned magn_energy = 0, sum_magn = 0;
       bool any_zero = false;
 #pragma unroll
       for (int j = 0; j < NSLOT; ++j) {
         const bool nyq = j == NSLOT - 1;
-        const uint32_t w = nyq ? nyq_w : v[j];
+        const int wre = nyq ? nyq_re : vr[j], wim = nyq ? 0 : vi[j];
         const int k = nyq ? HALF : lane + LANES * j;
-        re[j] = fx_lo(w);
-        im[j] = fx_s16(-fx_hi(w));
+        re[j] = wre;
+        im[j] = fx_s16(-wim);
         unsigned e;
         if (nyq || k == 0) {
           im[j] = 0;
           e = (unsigned)(re[j] * re[j]);
           magn[j] = (unsigned)(re[j] < 0 ? -re[j] : re[j]) & 0xffffu;
         } else {
-          e = (unsigned)(fx_lo(w) * fx_lo(w)) + (unsigned)(fx_hi(w) * fx_hi(w));
+          e = (unsigned)(wre * wre) + (unsigned)(wim * wim);
           magn[j] = fx_sqrt_floor(e) & 0xffffu;
         }
         const bool mine = nyq ? (lane == 0) : act;
@@ -1135,27 +1138,24 @@ nsx_process_kernel(const NsxLaunch p) {
           int src;
           if (ANA == 256) src = (int)(__brev((unsigned)pos) >> 24);
           else src = (int)(__brev((unsigned)pos) >> 25);
-          uint32_t w = 0;
+          vr[r] = vi[r] = 0;
           if (act) {
-            if (src <= HALF) {
-              w = buf[src];
-            } else {
-              const uint32_t m = buf[ANA - src];
-              w = fx_pack(fx_lo(m), fx_s16(-fx_hi(m)));
-            }
+            // (the mirrored half is the conjugate: real_fft.c:86-91)
+            const uint32_t m = buf[src <= HALF ? src : ANA - src];
+            vr[r] = fx_lo(m);
+            vi[r] = src <= HALF ? fx_hi(m) : fx_s16(-fx_hi(m));
           }
-          v[r] = w;
         }
       }
       __syncwarp();
-      const int out_cifft = fx_warp_cfft<true, ANA>(v, scr, s_tw, lane);
+      const int out_cifft = fx_warp_cfft<true, ANA>(vr, vi, scr, s_tw, lane);
 
       // ---- Denormalize (:476), gain (:1462-1496), SynthesisUpdate (:490)
       int y[8];
       int max_o16 = -1;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        y[r] = act ? fx_sat16(fx_shift_w32(fx_lo(v[r]), out_cifft - norm_data)) : 0;
+        y[r] = act ? fx_sat16(fx_shift_w32(vr[r], out_cifft - norm_data)) : 0;
         const int a16 = y[r] > 0 ? y[r] : fx_s16(-y[r]);
         if (act) max_o16 = a16 > max_o16 ? a16 : max_o16;
       }

@@ -54,8 +54,9 @@ enum : int {
 // Read-only tables (built by formula in nsx_host_init.h; the literal reference
 // tables they reproduce are cited there).
 // img[v] (v = 0: 256-point analysis, 1: 128-point) is the image of the kernel's per-CTA table block as
-// it sits in shared memory (window | twiddles | log2 fraction table), fetched with one TMA bulk copy.
-enum : int { kNsxTableImgWords = 128 + 128 + 128 };
+// it sits in shared memory (window | twiddles, packed | log2 fraction table | FFT twiddles as int2, regrouped
+// per stage: ns_fixed.cuh), fetched with one TMA bulk copy.
+enum : int { kNsxImgFftTw = 128 + 128 + 128, kNsxTableImgWords = kNsxImgFftTw + 2 * 252 };
 struct NsxTables {
   alignas(16) uint32_t img[2][kNsxTableImgWords];
   int16_t win256[256];
