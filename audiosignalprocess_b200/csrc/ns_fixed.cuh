@@ -75,26 +75,43 @@ NSB_DEV int fx_hi(uint32_t w) { return (int)(int16_t)(w >> 16); }
 // One butterfly on unpacked points a (kept) and x (twiddled), w = (cos, sin).
 // Forward: t = ((wr xr + ws xi + 1) >> 1, (wr xi - ws xr + 1) >> 1); out = (int16)((a 2^14 -+ t + 2^14) >> 15).
 // Inverse: t = ((wr xr - ws xi + 1) >> 1, (wr xi + ws xr + 1) >> 1); out = (int16)((a 2^14 -+ t + (2^13 << shift)) >> (14 + shift)).
-// Both as the upper half of the 32-bit sum scaled to put the kept bits at 16..31 (wrap-around included: the
-// discarded top bits are the ones the int16 cast discards).
+//
+// With p = the twiddle product incl. its + 1, floor((A + floor(p / 2)) / 2^k) = floor((2A + p) / 2^(k+1)) and
+// floor((A - floor(p / 2)) / 2^k) = floor((2A + 1 - p) / 2^(k+1)) for even A (a dropped or added odd unit never
+// crosses a multiple of an even divisor), so the halving disappears and each output is ONE multiply-add chain
+//   a * 2^15 + rounding (+ 1) +- wr xr +- ws xi
+// followed by one shift: the integer ALU pipe (shifts, adds, logic: half the rate of the multiply-add pipe, and
+// the pipe this kernel saturates) sees 4 instructions per butterfly instead of 12.  The int16 cast is the
+// upper half of the sum scaled to put the kept bits at 16..31 (wrap-around included: the bits shifted out are
+// the ones the cast discards).  The inverse transform at shift 2 keeps bit 31, cannot be doubled, and takes
+// the plain form.
 template <bool INV>
 NSB_DEV void fx_butterfly_u(int& ar, int& ai, int& xr, int& xi, int2 w, int shift) {
-  unsigned tr, ti;
-  if (INV) {
-    const int pr = w.x * xr - w.y * xi + 1, pi = w.x * xi + w.y * xr + 1;
-    tr = (unsigned)(pr >> 1) << (2 - shift);
-    ti = (unsigned)(pi >> 1) << (2 - shift);
+  if (!INV) {
+    const unsigned qr = (unsigned)(ar * 32768 + 32768), qi = (unsigned)(ai * 32768 + 32768);
+    const int mr = w.x * xr + w.y * xi, mi = w.x * xi - w.y * xr;     // p - 1
+    xr = (int)(qr - (unsigned)mr) >> 16;
+    xi = (int)(qi - (unsigned)mi) >> 16;
+    ar = (int)(qr + 1u + (unsigned)mr) >> 16;
+    ai = (int)(qi + 1u + (unsigned)mi) >> 16;
+  } else if (shift < 2) {
+    // scaled by 2^(1 - shift): a * 2^(16 - shift) + 2^15 (+ 2^(1 - shift)) +- (wr xr - ws xi) * 2^(1 - shift)
+    const int m = 2 - shift;                                      // 2 or 1
+    const int yr = xr * m, yi = xi * m;
+    const unsigned qr = (unsigned)(ar * (32768 * m) + 32768), qi = (unsigned)(ai * (32768 * m) + 32768);
+    const int mr = w.x * yr - w.y * yi, mi = w.x * yi + w.y * yr;
+    xr = (int)(qr - (unsigned)mr) >> 16;
+    xi = (int)(qi - (unsigned)mi) >> 16;
+    ar = (int)(qr + (unsigned)m + (unsigned)mr) >> 16;
+    ai = (int)(qi + (unsigned)m + (unsigned)mi) >> 16;
   } else {
-    const int pr = w.x * xr + w.y * xi + 1, pi = w.x * xi - w.y * xr + 1;
-    tr = (unsigned)pr & ~1u;
-    ti = (unsigned)pi & ~1u;
+    const int tr = (w.x * xr - w.y * xi + 1) >> 1, ti = (w.x * xi + w.y * xr + 1) >> 1;
+    const int qr = ar * 16384 + 32768, qi = ai * 16384 + 32768;
+    xr = (qr - tr) >> 16;
+    xi = (qi - ti) >> 16;
+    ar = (qr + tr) >> 16;
+    ai = (qi + ti) >> 16;
   }
-  const unsigned qr = ((unsigned)ar << (INV ? 16 - shift : 15)) + 32768u;
-  const unsigned qi = ((unsigned)ai << (INV ? 16 - shift : 15)) + 32768u;
-  xr = (int)(qr - tr) >> 16;
-  xi = (int)(qi - ti) >> 16;
-  ar = (int)(qr + tr) >> 16;
-  ai = (int)(qi + ti) >> 16;
 }
 
 // The inverse transform's scaling decision before a stage (complex_fft.c:186-198): the largest |value| of all

@@ -69,28 +69,29 @@ def measured_instructions(kernel, frames_per_launch, streams):
     return d["warp_instructions_per_unit"] if d else None
 
 
-def pcie_probe(torch, dev, mbytes=128, reps=6):
+def pcie_probe(torch, dev, seconds=1.0, mbytes=128):
     """Host<->device copy ceiling of THIS rank's GPU as the end-to-end path uses it: pinned buffers, an H2D
-    and a D2H copy in flight together on two streams.  Returns GB/s per direction (both directions move
-    `mbytes` per repetition at once)."""
+    and a D2H copy in flight together on two streams, SUSTAINED for `seconds` (the caller puts a barrier in
+    front, so under torchrun every rank copies during the same second: the ranks share the host's memory /
+    PCIe fabric, and a best-of-N of short bursts measures the moments the others were idle).  Returns the
+    mean GB/s per direction."""
     n = mbytes * 1000 * 1000 // 2
     h_in = torch.empty(n, dtype=torch.int16).pin_memory()
     h_out = torch.empty(n, dtype=torch.int16).pin_memory()
     d_a = torch.empty(n, dtype=torch.int16, device=dev)
     d_b = torch.empty(n, dtype=torch.int16, device=dev)
     s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    best = None
-    for _ in range(reps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    reps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
         with torch.cuda.stream(s1):
             d_a.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s2):
             h_out.copy_(d_b, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
-    return n * 2 / best / 1e9
+        reps += 1
+    return reps * n * 2 / (time.perf_counter() - t0) / 1e9
 
 
 def extra_leg(pkg, lib, torch, dev, stream, kind, fs, streams, F, mode, steps=10, warmup=3):
@@ -582,8 +583,8 @@ def main():
                "blocking_value": v_block, "blocking_api": "WebRtcNs%s_ProcessBatch, one call per step" % ("x" if a.fixed else ""),
                "pcie_gbs": gbs_dir, "pcie_probe_gbs": probe_total,
                "pcie_note": "GB/s per direction summed over the %d rank(s), both directions busy at once: what the end-to-end "
-                            "leg moved, and what a bare pinned-buffer H2D + D2H copy pair per rank reaches on this box at "
-                            "the same time" % world,
+                            "leg moved, and what bare pinned-buffer H2D + D2H copy pairs sustain for one second on all ranks "
+                            "at the same time (the ranks share the host's fabric: profiles/r2_pcie_probe_multi.log)" % world,
                "frac_of_pcie_probe": gbs_dir / probe_total if probe_total > 0 else None}
     sampler.stop_flag = True
     sampler.join(timeout=2)

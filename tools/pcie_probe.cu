@@ -32,8 +32,56 @@ __global__ void zc_kernel(const uint32_t* in, uint32_t* out, int n_streams, int 
   }
 }
 
-int main() {
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+// `pcie_probe dma [seconds]`: DMA copies only, each kind sustained for `seconds` (default 2) -- meant to be started
+// on several GPUs at once (one process per GPU, CUDA_VISIBLE_DEVICES), to see what the host fabric gives each GPU
+// when all of them copy: tools/pcie_probe_multi.sh.
+static double now_s() { struct timespec t; clock_gettime(CLOCK_REALTIME, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+int main(int argc, char** argv) {
   const int S = 4096, F = 100, FL = 160;
+  if (argc > 1 && strcmp(argv[1], "dma") == 0) {
+    const double secs = argc > 2 ? atof(argv[2]) : 2.0;
+    const size_t stride = (size_t)F * FL, bytes = S * stride * 2;
+    int16_t *h_in, *h_out, *d_in, *d_out;
+    CK(cudaMallocHost(&h_in, bytes)); CK(cudaMallocHost(&h_out, bytes));
+    CK(cudaMalloc(&d_in, bytes)); CK(cudaMalloc(&d_out, bytes));
+    memset(h_in, 1, bytes);
+    cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
+    // all processes start their phases on the same wall-clock marks
+    double t_mark = (double)((long)now_s() / 4 * 4 + 8);
+    const int cf = 25;   // 25-frame chunks: rows of 8000 bytes at a pitch of 32000, the host-pointer path's copies
+    for (int kind = 0; kind < 4; ++kind) {
+      while (now_s() < t_mark) usleep(200);
+      const double t0 = now_s();
+      long reps = 0;
+      while (now_s() - t0 < secs) {
+        if (kind == 0) {
+          CK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s1));
+          CK(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s2));
+        } else if (kind == 1) {
+          for (int f0 = 0; f0 < F; f0 += cf) {
+            CK(cudaMemcpy2DAsync(d_in + (size_t)f0 * FL * S, (size_t)cf * FL * 2, h_in + f0 * FL, stride * 2, (size_t)cf * FL * 2, S, cudaMemcpyHostToDevice, s1));
+            CK(cudaMemcpy2DAsync(h_out + f0 * FL, stride * 2, d_out + (size_t)f0 * FL * S, (size_t)cf * FL * 2, (size_t)cf * FL * 2, S, cudaMemcpyDeviceToHost, s2));
+          }
+        } else if (kind == 2) {
+          CK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s1));
+        } else {
+          CK(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s2));
+        }
+        CK(cudaStreamSynchronize(s1)); CK(cudaStreamSynchronize(s2));
+        ++reps;
+      }
+      const double dt = now_s() - t0;
+      static const char* names[4] = {"duplex 1-D (per direction)", "duplex 2-D rows 8000 B pitch 32000 (per direction)", "H2D 1-D alone", "D2H 1-D alone"};
+      printf("%-52s %6.1f GB/s\n", names[kind], reps * (double)bytes / dt * 1e-9);
+      fflush(stdout);
+      t_mark += secs + 2.0;
+    }
+    return 0;
+  }
   const size_t stride = (size_t)F * FL, bytes = S * stride * 2;
   int16_t *h_in, *h_out, *d_in, *d_out;
   CK(cudaMallocHost(&h_in, bytes)); CK(cudaMallocHost(&h_out, bytes));
