@@ -144,6 +144,7 @@ inline void nsf_fill_tables(Tables* t) {
   t->tw[160].x = -c8; t->tw[160].y = -c8;
   t->tw[224].x = c8;  t->tw[224].y = -c8;
   for (int i = 1; i < 132; ++i) t->logi[i] = (float)log((double)(float)i);
+  for (int i = 1; i < 132; ++i) t->logk_d[i] = log((double)i);
   // sequential float sums exactly as ns_core.c:1088-1100 accumulates them
   for (int v = 0; v < 2; ++v) {
     const int magn_len = v == 0 ? 129 : 65;

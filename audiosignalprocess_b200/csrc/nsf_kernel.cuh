@@ -669,7 +669,7 @@ nsf_process_kernel(const NsfLaunch p) {
             int kub = k < 5 ? 5 : k;
             asm volatile("" : "+r"(kub));
             const float ub = (float)kub;
-            parametric[j] = nsb_div_pow_rn(pnum, ub, pexp);   // (float)(parametric_num / pow(use_band, parametric_exp))
+            parametric[j] = nsb_div_pow_rn(pnum, ub, T->logk_d[kub], pexp);   // (float)(parametric_num / pow(use_band, parametric_exp))
           }
           noise[j] *= (float)blockInd;
           const float t = parametric[j] * (float)(50 - blockInd);

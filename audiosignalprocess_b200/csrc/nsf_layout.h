@@ -73,6 +73,7 @@ struct NsfTables {
   float logi[132];    // (float)log((float)i), i >= 1
   float sum_log_i[2];     // [0]: magnLen 129, [1]: magnLen 65   (ns_core.c:1093-1095)
   float sum_log_i_sq[2];
+  double logk_d[132];     // log(k) in double, k >= 1: the start-up frames' pow(k, exp) = e^(exp log k)
 };
 
 struct NsfLaunch {

@@ -5,9 +5,12 @@ lquantile| < WIDTH: ns_core.c:243,252 -- 774 per frame); one that goes the other
 whole tracker step and the output leaves the 1e-4 FS / 90 dB tolerance for seconds.  The kernel therefore
 reproduces the reference's forward FFT rounding for rounding and takes the tracker's logarithm as the
 rounded double-precision one (csrc/ns_warp.cuh ooura_fwd, nsb_log_rn).  What that buys is checked here:
-after thousands of frames the three log-quantile trackers, their densities and the magnitude spectrum of
-the last frame are IDENTICAL to the fields of the reference's struct, and the continuous quantities
-(noise, gains, probabilities) agree to a few ulp."""
+after thousands of frames every field of the recursion -- the three log-quantile trackers and their densities,
+the noise quantile, the Wiener gains, the previous noise and magnitude spectra, the LRT average, the pause
+spectrum, the seven features, the model parameters re-estimated every 500 frames and the prior speech
+probability -- is IDENTICAL to the field of the reference's struct.  (The double-precision library functions
+behind log / exp / tanh differ from glibc's in the last place of a double; rounded to float that shows once
+in ~2^28 evaluations, a one-ulp ripple that dies out within a few frames.)"""
 import numpy as np
 import pytest
 
@@ -30,19 +33,14 @@ def test_tracker_state_is_the_reference_struct(nslib, reflib, fs, mode, frames, 
         f0 += nf
         ci += 1
     lib = nslib.load_library()
-    worst = {}
     for s in range(n):
         _, tr = ref_ns_trace(reflib, fs, mode, x[s])
         g = gpu_nsf_state(lib, b._handles[s], fs)
-        for key in ("lquantile", "density", "magn"):
+        # the whole decision-directed recursion: trackers, densities, noise quantile, Wiener gains, previous noise
+        # and magnitude, LRT average, pause spectrum, the seven features, the model parameters and the prior
+        for key in ("lquantile", "density", "magn", "quantile", "smooth", "noisePrev", "logLrt", "magnAvgPause",
+                    "featureData", "priorModelPars"):
             assert bits_equal(g[key], tr[key][-1]), "stream %d: %s differs from the reference struct (max |d| %g)" % (
-                s, key, np.abs(g[key] - tr[key][-1]).max())
-        # continuous quantities: a few ulp (single-precision exp / tanh / tree sums on the device)
-        for key in ("quantile", "smooth", "noisePrev", "logLrt", "magnAvgPause"):
-            ref = tr[key][-1]
-            rel = float(np.max(np.abs(g[key] - ref) / np.maximum(np.abs(ref), 1e-3)))
-            worst[key] = max(worst.get(key, 0.0), rel)
-        assert abs(g["prior"] - float(tr["prior"][-1])) <= 1e-5
-    print("worst relative deviation of the continuous state:", {k: "%.2e" % v for k, v in worst.items()})
-    assert max(worst.values()) <= 1e-4
+                s, key, np.abs(np.asarray(g[key], np.float64) - tr[key][-1]).max())
+        assert g["prior"] == float(tr["prior"][-1])
     b.close()
