@@ -69,11 +69,98 @@ struct NsfGeo {
   static constexpr int kNC = ANA / 2;           // complex points
   static constexpr int kL = kNC / 4;            // FFT lanes
   static constexpr int kSlots = kNC / 32 + 1;   // bins per lane incl. Nyquist slot
+  static constexpr int kPairs = kNC / 64;       // slot pairs (2g, 2g+1) worked on packed; the Nyquist slot stays scalar
   static constexpr int kFP = kFrame / 2;        // frame sample pairs (80 / 40)
   static constexpr int kHP = (ANA - kFrame) / 2;  // history pairs (48 / 24)
   static constexpr int kTP = ANA / 2;           // all pairs
   static constexpr int kStg = ANA == 256 ? 132 : 68;   // words per staging array of chain_sum4: >= kBins, = 4 (mod 32)
 };
+
+// ---- the per-bin phases, written once for one bin (T = float: the Nyquist slot) and for two
+// (T = float2: slot pairs, packed arithmetic -- ns_warp.cuh)
+#define NSF_PAIR(a, g) make_float2((a)[2 * (g)], (a)[2 * (g) + 1])
+#define NSF_UNPAIR(a, g, v) ((a)[2 * (g)] = (v).x, (a)[2 * (g) + 1] = (v).y)
+
+// ComputeSnr (ns_core.c:566-588) and the first loop of SpeechNoiseProb (:660-679), plus the terms of
+// covMagnPause, varPause, varMagn (:620-626)
+template <class T>
+NSB_DEV void nsf_snr_lrt(T magn, T noise, T noisePrev, T magnPrevA, T smoothPrev, T mpause, float avgMagn,
+                         float avgPause, T& prevEst, T& logLrt, T& dmdp, T& dpdp, T& dmdm) {
+  const T eps = vbcast(0.0001f, T()), one = vbcast(1.f, T());
+  prevEst = vmul(vfdiv(magnPrevA, vadd(noisePrev, eps)), smoothPrev);
+  const T post = vadd(vfdiv(magn, vadd(noise, eps)), vbcast(-1.f, T()));
+  const T snrPost = vsel(vgt(magn, noise), post, vbcast(0.f, T()));
+  const T snrPrior = vmmadd(vbcast(0.98f, T()), prevEst, vbcast(1.f - 0.98f, T()), snrPost);
+  const T sp2 = vadd(snrPrior, snrPrior);   // 2 * snrPrior
+  const T t1 = vadd(one, sp2);
+  const T t2 = vfdiv(sp2, vadd(t1, eps));
+  // besselTmp - log(t1): a product into a sum, so through vmadd; the product by 0.5 after it is exact --
+  // contracted into the last sum or not, the same bits
+  const T d = vsub(vmadd(vadd(snrPost, one), t2, vneg(vlog_rn(t1))), logLrt);
+  logLrt = vadd(logLrt, vmul(vbcast(0.5f, T()), d));
+  const T dm = vadd(magn, vbcast(-avgMagn, T())), dp = vadd(mpause, vbcast(-avgPause, T()));
+  dmdp = vmul(dm, dp);
+  dpdp = vmul(dp, dp);
+  dmdm = vmul(dm, dm);
+}
+
+// UpdateNoiseEstimate for one bin / two bins (ns_core.c:800-846); prevHigh: the previous bin's speech
+// probability exceeds 0.2 (false at bin 0).  When the old and the new smoothing factor agree the second
+// estimate is the first one, bit for bit, so the reference's branch is a minimum.
+template <class T, class M>
+NSB_DEV void nsf_noise_update(T ps, M prevHigh, T magn, T noisePrev, T& mpause, T& noise) {
+  const T one = vbcast(1.f, T()), thr = vbcast(0.2f, T());
+  const T hi = vbcast(0.99f, T()), lo = vbcast(0.9f, T()), chi = vbcast(1.f - 0.99f, T()), clo = vbcast(1.f - 0.9f, T());
+  const T pn = vsub(one, ps);
+  const T mix = vmmadd(pn, magn, ps, noisePrev);
+  const T nTmp = vmmadd(vsel(prevHigh, hi, lo), noisePrev, vsel(prevHigh, chi, clo), mix);
+  const M high = vgt(ps, thr);
+  const T nz2 = vmmadd(vsel(high, hi, lo), noisePrev, vsel(high, chi, clo), mix);
+  mpause = vsel(vlt(ps, thr), vmadd(vbcast(0.05f, T()), vsub(magn, mpause), mpause), mpause);
+  noise = vsel(vlt(nTmp, nz2), nTmp, nz2);
+}
+
+// ComputeDdBasedWienerFilter with the flooring of ProcessCore (ns_core.c:985-1007, :1268-1274)
+template <class T>
+NSB_DEV T nsf_wiener_gain(T magn, T noise, T prevEst, float overdrive, float denoiseBound) {
+  const T one = vbcast(1.f, T()), db = vbcast(denoiseBound, T());
+  const T post = vadd(vfdiv(magn, vadd(noise, vbcast(0.0001f, T()))), vbcast(-1.f, T()));
+  const T cur_est = vsel(vgt(magn, noise), post, vbcast(0.f, T()));
+  const T sp = vmmadd(vbcast(0.98f, T()), prevEst, vbcast(1.f - 0.98f, T()), cur_est);
+  T g = vfdiv(sp, vadd(vbcast(overdrive, T()), sp));
+  g = vsel(vlt(g, db), db, g);
+  return vsel(vgt(g, one), one, g);
+}
+
+// One bin's (T = float) or two bins' (T = float2, packed arithmetic) three quantile trackers, ns_core.c:236-259.
+// The step carries its sign through the division (round-to-nearest is symmetric), so the update is one addition.
+// `chain` advances `adv` steps after each tracker: the sequential sums of pass A need none of this.
+template <class T, class Chain>
+NSB_DEV void nsf_tracker_update(const T lm, T (&lq)[3], T (&dn)[3], const float (&c1)[3], const float (&rc1)[3],
+                                const float (&cf)[3], Chain& chain, int adv) {
+  const T one = vbcast(1.f, T()), forty = vbcast(40.f, T());
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const T vc1 = vbcast(c1[s], T()), vrc1 = vbcast(rc1[s], T());
+    const T delta = vsel(vgt(dn[s], one), vfdiv(forty, dn[s]), forty);
+    // one division: QUANTILE*delta/(c+1) upwards, (1-QUANTILE)*delta/(c+1) downwards
+    const T w = vsel(vgt(lm, lq[s]), vbcast(0.25f, T()), vbcast(-(1.f - 0.25f), T()));
+    lq[s] = vadd(lq[s], vfdiv_r(vmul(w, delta), vc1, vrc1));
+    const T upd = vfdiv_r(vmadd(vbcast(cf[s], T()), dn[s], vbcast(1.f / (2.f * 0.01f), T())), vc1, vrc1);
+    dn[s] = vsel(vlt(vabs(vsub(lm, lq[s])), vbcast(0.01f, T())), upd, dn[s]);
+    chain.advance(adv);
+  }
+}
+
+// The reference's real-input split seen from one bin (fft4g.c:1234-1256): zk, zm the complex transform at
+// k and N/2 - k, w = s_split[k]:  (xd, xs) = (zk.x - zm.x, zk.y + zm.y),
+// re = zk.x - (w.x xd - w.y xs), im = zk.y - (w.x xs + w.y xd) -- on (re, im) pairs, four packed operations
+// and the two sums of products that must stay scalar (ns_warp.cuh vmadd).
+NSB_DEV float2 nsf_real_split(float2 zk, float2 zm, float2 w) {
+  const float2 x = vadd(zk, make_float2(-zm.x, zm.y));
+  const float2 m1 = vmul(x, make_float2(w.x, w.x)), m2 = vmul(x, make_float2(w.y, w.y));
+  return vadd(zk, make_float2(-(m1.x - m2.y), -(m1.y + m2.x)));
+}
 
 NSB_DEV int pad_idx(int k) { return k + ((k >> 6) << 1); }
 
@@ -451,9 +538,9 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 w = reinterpret_cast<const float2*>(s_win)[lane + G::kL * j];
-        v[j].x *= w.x;
-        v[j].y *= w.y;
-        energy1 += v[j].x * v[j].x + v[j].y * v[j].y;
+        v[j] = vmul(v[j], w);
+        const float2 sq = vmul(v[j], v[j]);
+        energy1 += sq.x + sq.y;
       }
     }
     // Energy (ns_core.c:951) is a sum of squares: zero iff every term is, so the zero-input test is
@@ -508,24 +595,43 @@ nsf_process_kernel(const NsfLaunch p) {
           // (wr, wi) = s_split[k] -- wi negated on the mirror side, (0, +-1/2) at bins 0 and N/2 so that
           // the same expression yields a[0] +- a[1] -- the same additions and products, rounding for rounding
           const float2 w = s_split[k];
-          const float xd = zk.x - zm.x, xs = zk.y + zm.y;
-          re[j] = zk.x - (w.x * xd - w.y * xs);
-          im[j] = zk.y - (w.x * xs + w.y * xd);
-          if (nyq || k == 0) im[j] = 0.f;
-          const float e = re[j] * re[j] + im[j] * im[j];
-          magn[j] = nsb_sqrtf_p1(e);
-          lmagn[j] = nsb_log_rn(magn[j]);   // (float)log((double)magn): ns_core.c:228
+          const float2 X = nsf_real_split(zk, zm, w);
+          re[j] = X.x;
+          im[j] = (nyq || k == 0) ? 0.f : X.y;
           const float4 r2 = *reinterpret_cast<const float4*>(B + k * kNsfBinRec + 8);  // noisePrev magnPrev logLrt pause
           noisePrev[j] = r2.x;
           magnPrevA[j] = r2.y;
           logLrt[j] = r2.z;
           mpause[j] = r2.w;
-          // terms of the four sums of pass A (below), bin by bin
-          if (!nyq || lane == 0) {
-            stg[k] = e;                                   // signalEnergy   ns_core.c:1090
-            stg[G::kStg + k] = magn[j];                   // sumMagn        :1091
-            stg[2 * G::kStg + k] = k == 0 ? 0.f : lmagn[j];   // flatness numerator, bins >= 1   :540-542
-            stg[3 * G::kStg + k] = r2.w;                  // avgPause       :609
+          if (!nyq || lane == 0) stg[3 * G::kStg + k] = r2.w;   // avgPause       ns_core.c:609
+        }
+        // magnitudes, their logarithms (float)log((double)magn) (ns_core.c:228) and the terms of the other
+        // three sums of pass A (below), bin by bin
+#pragma unroll
+        for (int g = 0; g < G::kPairs; ++g) {
+          const float2 re2 = NSF_PAIR(re, g), im2 = NSF_PAIR(im, g);
+          const float2 e = vmmadd(re2, re2, im2, im2);
+          const float2 m = vsqrt_p1(e);
+          const float2 lm = vlog_rn(m);
+          NSF_UNPAIR(magn, g, m);
+          NSF_UNPAIR(lmagn, g, lm);
+          const int k = lane + 64 * g;
+          stg[k] = e.x;                                   // signalEnergy   :1090
+          stg[k + 32] = e.y;
+          stg[G::kStg + k] = m.x;                         // sumMagn        :1091
+          stg[G::kStg + k + 32] = m.y;
+          stg[2 * G::kStg + k] = k == 0 ? 0.f : lm.x;     // flatness numerator, bins >= 1   :540-542
+          stg[2 * G::kStg + k + 32] = lm.y;
+        }
+        {
+          constexpr int j = G::kSlots - 1;
+          const float e = re[j] * re[j] + im[j] * im[j];
+          magn[j] = nsb_sqrtf_p1(e);
+          lmagn[j] = nsb_log_rn(magn[j]);
+          if (lane == 0) {
+            stg[G::kNC] = e;
+            stg[G::kStg + G::kNC] = magn[j];
+            stg[2 * G::kStg + G::kNC] = lmagn[j];
           }
         }
         __syncwarp();  // every lane has read its mirrored points: scratch is free again
@@ -561,33 +667,38 @@ nsf_process_kernel(const NsfLaunch p) {
         rc1[s] = frcp_nr(c1[s]);
         cf[s] = (float)cnt[s];
       }
+      // slot pairs (bins lane + 64 g and lane + 64 g + 32) run packed, the Nyquist slot scalar
 #pragma unroll
-      for (int j = 0; j < G::kSlots; ++j) {
-        const bool nyq = (j == G::kSlots - 1);
-        const int k = nyq ? G::kNC : lane + 32 * j;
-        float* R = B + k * kNsfBinRec;
-        float4 r0 = *reinterpret_cast<float4*>(R);      // lq0 lq1 lq2 dens0
-        float4 r1 = *reinterpret_cast<float4*>(R + 4);  // dens1 dens2 quantile smooth
+      for (int g = 0; g < G::kPairs; ++g) {
+        float* Ra = B + (lane + 64 * g) * kNsfBinRec;
+        float* Rb = Ra + 32 * kNsfBinRec;
+        const float4 a0 = *reinterpret_cast<float4*>(Ra), a1 = *reinterpret_cast<float4*>(Ra + 4);
+        const float4 b0 = *reinterpret_cast<float4*>(Rb), b1 = *reinterpret_cast<float4*>(Rb + 4);
+        float2 lq[3] = {make_float2(a0.x, b0.x), make_float2(a0.y, b0.y), make_float2(a0.z, b0.z)};
+        float2 dn[3] = {make_float2(a0.w, b0.w), make_float2(a1.x, b1.x), make_float2(a1.y, b1.y)};
+        smoothPrev[2 * g] = a1.w;
+        smoothPrev[2 * g + 1] = b1.w;
+        nsf_tracker_update(make_float2(lmagn[2 * g], lmagn[2 * g + 1]), lq, dn, c1, rc1, cf, chainA, 4);
+        noise[2 * g] = a1.z;
+        noise[2 * g + 1] = b1.z;
+        *reinterpret_cast<float4*>(Ra) = make_float4(lq[0].x, lq[1].x, lq[2].x, dn[0].x);
+        // whole 16-byte groups only: scalar accesses at a 12-word lane stride are 4-way bank conflicts
+        *reinterpret_cast<float4*>(Ra + 4) = make_float4(dn[1].x, dn[2].x, a1.z, a1.w);
+        *reinterpret_cast<float4*>(Rb) = make_float4(lq[0].y, lq[1].y, lq[2].y, dn[0].y);
+        *reinterpret_cast<float4*>(Rb + 4) = make_float4(dn[1].y, dn[2].y, b1.z, b1.w);
+      }
+      {
+        float* R = B + G::kNC * kNsfBinRec;
+        const float4 r0 = *reinterpret_cast<float4*>(R);      // lq0 lq1 lq2 dens0
+        const float4 r1 = *reinterpret_cast<float4*>(R + 4);  // dens1 dens2 quantile smooth
         float lq[3] = {r0.x, r0.y, r0.z};
         float dn[3] = {r0.w, r1.x, r1.y};
-        float quant = r1.z;
-        smoothPrev[j] = r1.w;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const float delta = dn[s] > 1.f ? fdiv(40.f, dn[s]) : 40.f;
-          // one division: QUANTILE*delta/(c+1) upwards, (1-QUANTILE)*delta/(c+1) downwards
-          const bool up = lmagn[j] > lq[s];
-          const float step = fdiv_r((up ? 0.25f : (1.f - 0.25f)) * delta, c1[s], rc1[s]);
-          lq[s] = up ? lq[s] + step : lq[s] - step;
-          if (fabsf(lmagn[j] - lq[s]) < 0.01f)
-            dn[s] = fdiv_r(cf[s] * dn[s] + 1.f / (2.f * 0.01f), c1[s], rc1[s]);
-          chainA.advance(2);
-        }
-        noise[j] = quant;
-        if (!nyq || lane == 0) {
+        smoothPrev[G::kSlots - 1] = r1.w;
+        nsf_tracker_update(lmagn[G::kSlots - 1], lq, dn, c1, rc1, cf, chainA, 4);
+        noise[G::kSlots - 1] = r1.z;
+        if (lane == 0) {
           *reinterpret_cast<float4*>(R) = make_float4(lq[0], lq[1], lq[2], dn[0]);
-          // whole 16-byte groups only: scalar accesses at a 12-word lane stride are 4-way bank conflicts
-          *reinterpret_cast<float4*>(R + 4) = make_float4(dn[1], dn[2], quant, r1.w);
+          *reinterpret_cast<float4*>(R + 4) = make_float4(dn[1], dn[2], r1.z, r1.w);
         }
       }
       float sigE, sumMagn, sumLog, sumPause;
@@ -688,29 +799,36 @@ nsf_process_kernel(const NsfLaunch p) {
 
       // ---- (g) ComputeSnr (ns_core.c:566-588) and the first loop of SpeechNoiseProb (:660-679): neither needs
       // anything from FeatureUpdate, and the sum over the updated logLrtTimeAvg rides in pass B
-      float snrPrior[G::kSlots], snrPost[G::kSlots];
       const float avgPause = NSB_FDIV_C(sumPause, kMagnLenF);
       const float avgMagn = NSB_FDIV_C(sumMagn, kMagnLenF);
 #pragma unroll
-      for (int j = 0; j < G::kSlots; ++j) {
-        const bool nyq = (j == G::kSlots - 1);
-        const int k = nyq ? G::kNC : lane + 32 * j;
-        prevEst[j] = fdiv(magnPrevA[j], noisePrev[j] + 0.0001f) * smoothPrev[j];
-        // branch-free: a branch per slot would fence the five division chains off from each other
-        const float post = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
-        snrPost[j] = magn[j] > noise[j] ? post : 0.f;
-        snrPrior[j] = 0.98f * prevEst[j] + (1.f - 0.98f) * snrPost[j];
-        const float t1 = 1.f + 2.f * snrPrior[j];
-        const float t2 = fdiv(2.f * snrPrior[j], t1 + 0.0001f);
-        const float bessel = (snrPost[j] + 1.f) * t2;
-        logLrt[j] += 0.5f * (bessel - nsb_log_rn(t1) - logLrt[j]);
+      for (int g = 0; g < G::kPairs; ++g) {
+        float2 pe, ll = NSF_PAIR(logLrt, g), dmdp, dpdp, dmdm;
+        nsf_snr_lrt(NSF_PAIR(magn, g), NSF_PAIR(noise, g), NSF_PAIR(noisePrev, g), NSF_PAIR(magnPrevA, g),
+                    NSF_PAIR(smoothPrev, g), NSF_PAIR(mpause, g), avgMagn, avgPause, pe, ll, dmdp, dpdp, dmdm);
+        NSF_UNPAIR(prevEst, g, pe);
+        NSF_UNPAIR(logLrt, g, ll);
         // terms of the four sums of pass B (ComputeSpectralDifference :620-626, SpeechNoiseProb :678)
-        const float dm = magn[j] - avgMagn, dp = mpause[j] - avgPause;
-        if (!nyq || lane == 0) {
-          stg[k] = dm * dp;
-          stg[G::kStg + k] = dp * dp;
-          stg[2 * G::kStg + k] = dm * dm;
-          stg[3 * G::kStg + k] = logLrt[j];
+        const int k = lane + 64 * g;
+        stg[k] = dmdp.x;
+        stg[k + 32] = dmdp.y;
+        stg[G::kStg + k] = dpdp.x;
+        stg[G::kStg + k + 32] = dpdp.y;
+        stg[2 * G::kStg + k] = dmdm.x;
+        stg[2 * G::kStg + k + 32] = dmdm.y;
+        stg[3 * G::kStg + k] = ll.x;
+        stg[3 * G::kStg + k + 32] = ll.y;
+      }
+      {
+        constexpr int j = G::kSlots - 1;
+        float dmdp, dpdp, dmdm;
+        nsf_snr_lrt(magn[j], noise[j], noisePrev[j], magnPrevA[j], smoothPrev[j], mpause[j], avgMagn, avgPause,
+                    prevEst[j], logLrt[j], dmdp, dpdp, dmdm);
+        if (lane == 0) {
+          stg[G::kNC] = dmdp;
+          stg[G::kStg + G::kNC] = dpdp;
+          stg[2 * G::kStg + G::kNC] = dmdm;
+          stg[3 * G::kStg + G::kNC] = logLrt[j];
         }
       }
       __syncwarp();
@@ -815,17 +933,19 @@ nsf_process_kernel(const NsfLaunch p) {
         Hw[kH_priorSpeechProb] = prior;
         const float gainPrior = fdiv(1.f - prior, prior + 0.0001f);
 #pragma unroll
-        for (int j = 0; j < G::kSlots; ++j) {
-          const float inv = gainPrior * invLrt[j];
-          prob[j] = fdiv(1.f, 1.f + inv);
+        for (int g = 0; g < G::kPairs; ++g) {
+          const float2 pr = vfdiv(make_float2(1.f, 1.f), vmadd(make_float2(gainPrior, gainPrior), NSF_PAIR(invLrt, g), make_float2(1.f, 1.f)));
+          NSF_UNPAIR(prob, g, pr);
         }
+        prob[G::kSlots - 1] = fdiv(1.f, 1.f + gainPrior * invLrt[G::kSlots - 1]);
       }
 
       // ---- (j) UpdateNoiseEstimate (ns_core.c:800-846): gamma carried from bin i-1
+      bool prevHigh[G::kSlots];   // the speech probability of bin k-1 exceeds 0.2 (false at bin 0)
 #pragma unroll
       for (int j = 0; j < G::kSlots; ++j) {
         const bool nyq = (j == G::kSlots - 1);
-        float pprev;  // speech probability of bin k-1
+        float pprev;
         if (nyq) {
           pprev = __shfl_sync(kFullMask, prob[G::kSlots - 2], 31);
         } else {
@@ -833,21 +953,19 @@ nsf_process_kernel(const NsfLaunch p) {
           const float wrap = __shfl_sync(kFullMask, prob[j > 0 ? j - 1 : 0], 31);
           if (lane == 0) pprev = wrap;
         }
-        const bool first = (!nyq && j == 0 && lane == 0);
-        const float gOld = (!first && pprev > 0.2f) ? 0.99f : 0.9f;
-        const float ps = prob[j], pn = 1.f - ps;
-        const float mix = pn * magn[j] + ps * noisePrev[j];
-        const float nTmp = gOld * noisePrev[j] + (1.f - gOld) * mix;
-        const float gNew = ps > 0.2f ? 0.99f : 0.9f;
-        if (ps < 0.2f) mpause[j] += 0.05f * (magn[j] - mpause[j]);
-        float nz;
-        if (gNew == gOld) {
-          nz = nTmp;
-        } else {
-          nz = gNew * noisePrev[j] + (1.f - gNew) * mix;
-          if (nTmp < nz) nz = nTmp;
-        }
-        noise[j] = nz;
+        prevHigh[j] = !(!nyq && j == 0 && lane == 0) && pprev > 0.2f;
+      }
+#pragma unroll
+      for (int g = 0; g < G::kPairs; ++g) {
+        float2 mp = NSF_PAIR(mpause, g), nz;
+        const bool2v ph = {prevHigh[2 * g], prevHigh[2 * g + 1]};
+        nsf_noise_update(NSF_PAIR(prob, g), ph, NSF_PAIR(magn, g), NSF_PAIR(noisePrev, g), mp, nz);
+        NSF_UNPAIR(mpause, g, mp);
+        NSF_UNPAIR(noise, g, nz);
+      }
+      {
+        constexpr int j = G::kSlots - 1;
+        nsf_noise_update(prob[j], prevHigh[j], magn[j], noisePrev[j], mpause[j], noise[j]);
       }
       if (SPLIT) {
         // ns_core.c:1178-1180 and the fields Process reads later: noise, magnPrevAnalyze,
@@ -891,9 +1009,9 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 w = reinterpret_cast<const float2*>(s_win)[lane + G::kL * j];
-          v[j].x *= w.x;
-          v[j].y *= w.y;
-          energy1 += v[j].x * v[j].x + v[j].y * v[j].y;
+          v[j] = vmul(v[j], w);
+          const float2 sq = vmul(v[j], v[j]);
+          energy1 += sq.x + sq.y;
         }
       }
       energy1 = warp_sum(energy1);
@@ -916,10 +1034,9 @@ nsf_process_kernel(const NsfLaunch p) {
           // (wr, wi) = s_split[k] -- wi negated on the mirror side, (0, +-1/2) at bins 0 and N/2 so that
           // the same expression yields a[0] +- a[1] -- the same additions and products, rounding for rounding
           const float2 w = s_split[k];
-          const float xd = zk.x - zm.x, xs = zk.y + zm.y;
-          re[j] = zk.x - (w.x * xd - w.y * xs);
-          im[j] = zk.y - (w.x * xs + w.y * xd);
-          if (nyq || k == 0) im[j] = 0.f;
+          const float2 X = nsf_real_split(zk, zm, w);
+          re[j] = X.x;
+          im[j] = (nyq || k == 0) ? 0.f : X.y;
           magn[j] = nsb_sqrtf_p1(re[j] * re[j] + im[j] * im[j]);
           const float* R = B + k * kNsfBinRec;
           noise[j] = X_noise[k];
@@ -956,15 +1073,11 @@ nsf_process_kernel(const NsfLaunch p) {
       // ---- (k) Wiener filter, flooring, start-up blend (ns_core.c:985-1007, 1268-1307)
       float gainW[G::kSlots];
 #pragma unroll
-      for (int j = 0; j < G::kSlots; ++j) {
-        const float post = fdiv(magn[j], noise[j] + 0.0001f) - 1.f;
-        const float cur_est = magn[j] > noise[j] ? post : 0.f;
-        const float sp = 0.98f * prevEst[j] + (1.f - 0.98f) * cur_est;
-        float g = fdiv(sp, overdrive + sp);
-        if (g < denoiseBound) g = denoiseBound;
-        if (g > 1.f) g = 1.f;
-        gainW[j] = g;
+      for (int g = 0; g < G::kPairs; ++g) {
+        const float2 gw = nsf_wiener_gain(NSF_PAIR(magn, g), NSF_PAIR(noise, g), NSF_PAIR(prevEst, g), overdrive, denoiseBound);
+        NSF_UNPAIR(gainW, g, gw);
       }
+      gainW[G::kSlots - 1] = nsf_wiener_gain(magn[G::kSlots - 1], noise[G::kSlots - 1], prevEst[G::kSlots - 1], overdrive, denoiseBound);
       // the start-up blend sits outside the per-slot loops: a (warp-uniform) branch inside them
       // would fence the slots' division chains off from each other
       if (blockInd < 50) {
@@ -991,8 +1104,7 @@ nsf_process_kernel(const NsfLaunch p) {
         const int k = nyq ? G::kNC : lane + 32 * j;
         const float flt = gainW[j];
         float2 z = scr[k];   // written by this lane (the Nyquist point by lane 0)
-        z.x *= flt;
-        z.y *= flt;
+        z = vmul(z, make_float2(flt, flt));
         if (!nyq || lane == 0) {
           float* R = B + k * kNsfBinRec;
           R[kB_smooth] = flt;
@@ -1055,7 +1167,8 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
       for (int u = 0; u < kTU; ++u) {
         y[u] = scr[pad_idx(lane + 32 * u)];
-        energy2 += y[u].x * y[u].x + y[u].y * y[u].y;
+        const float2 sq = vmul(y[u], y[u]);
+        energy2 += sq.x + sq.y;
       }
       constexpr float kIfftScale = 1.f / (float)ANA;   // (2 / N) / 2: what y above still lacks
       float factor = 1.f;
@@ -1079,7 +1192,7 @@ nsf_process_kernel(const NsfLaunch p) {
 #pragma unroll
       for (int u = 0; u < kTU; ++u) {
         const float2 w = reinterpret_cast<const float2*>(s_win)[lane + 32 * u];
-        y[u] = make_float2(fscaled * (w.x * y[u].x), fscaled * (w.y * y[u].y));
+        y[u] = vmul(make_float2(fscaled, fscaled), vmul(w, y[u]));
       }
       __syncwarp();
 #pragma unroll
@@ -1093,8 +1206,7 @@ nsf_process_kernel(const NsfLaunch p) {
           o = scr[pr];
           if (pr < G::kHP) {
             const float2 t = ovl[pr];
-            o.x += t.x;
-            o.y += t.y;
+            o = vadd(o, t);
             ovl[pr] = scr[G::kFP + pr];
           }
         }
@@ -1159,7 +1271,7 @@ nsf_process_kernel(const NsfLaunch p) {
           const int pr = lane + 32 * u;
           if (pr < G::kFP) {
             float2 o = blk[pr];
-            if (hbApplyGain) { o.x *= hbGain; o.y *= hbGain; }
+            if (hbApplyGain) o = vmul(o, make_float2(hbGain, hbGain));
             store_pair(f, b + 1, pr, I16 ? o : make_float2(sat_s16f(o.x), sat_s16f(o.y)));
           }
         }

@@ -5,7 +5,7 @@ for cfg in $2; do
   IFS=: read F n steps extra <<< "$cfg"
   for v in $1; do
     lib=$PWD/audiosignalprocess_b200/variants/lib$v.so; [ $v = main ] && lib=$PWD/audiosignalprocess_b200/libwebrtc_ns_b200.so
-    NSB200_LIB=$lib timeout 300 python bench.py --steps $steps --warmup 5 --no-e2e --no-cpu --frames-per-step $F --streams $n $extra 2>/dev/null | python -c "
+    NSB200_LIB=$lib timeout 300 python bench.py --steps $steps --warmup 5 --no-e2e --no-cpu --no-extra --no-tick --frames-per-step $F --streams $n $extra 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
