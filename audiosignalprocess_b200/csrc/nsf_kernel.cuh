@@ -154,12 +154,11 @@ NSB_DEV void nsf_tracker_update(const T lm, T (&lq)[3], T (&dn)[3], const float 
 
 // The reference's real-input split seen from one bin (fft4g.c:1234-1256): zk, zm the complex transform at
 // k and N/2 - k, w = s_split[k]:  (xd, xs) = (zk.x - zm.x, zk.y + zm.y),
-// re = zk.x - (w.x xd - w.y xs), im = zk.y - (w.x xs + w.y xd) -- on (re, im) pairs, four packed operations
-// and the two sums of products that must stay scalar (ns_warp.cuh vmadd).
+// re = zk.x - (w.x xd - w.y xs), im = zk.y - (w.x xs + w.y xd) -- on (re, im) pairs: five packed operations.
 NSB_DEV float2 nsf_real_split(float2 zk, float2 zm, float2 w) {
   const float2 x = vadd(zk, make_float2(-zm.x, zm.y));
-  const float2 m1 = vmul(x, make_float2(w.x, w.x)), m2 = vmul(x, make_float2(w.y, w.y));
-  return vadd(zk, make_float2(-(m1.x - m2.y), -(m1.y + m2.x)));
+  const float2 in = cmul_parts(w.x, x, w.y, x);   // (w.x xd - w.y xs, w.x xs + w.y xd)
+  return vadd(zk, make_float2(-in.x, -in.y));
 }
 
 NSB_DEV int pad_idx(int k) { return k + ((k >> 6) << 1); }

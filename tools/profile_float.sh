@@ -8,5 +8,6 @@ ncu --set full --clock-control none --import-source on -k regex:nsf_process -s 4
 python tools/ncu_summary.py kernel $O/${tag}_prof_float.ncu-rep $O/${tag}_nsf_kernel_F100.md $O/${tag}_nsf_kernel_F100.json 409600 > /dev/null
 python tools/ncu_lines.py $O/${tag}_prof_float.ncu-rep 409600 4 > $O/${tag}_nsf_kernel_F100_lines.txt 2>&1
 cat $O/${tag}_nsf_kernel_F100.md | head -60
+python tools/ncu_opcodes.py $O/${tag}_prof_float.ncu-rep 409600 > $O/${tag}_nsf_kernel_F100_opcodes.txt 2>&1
 [ -z "$KEEP_REPS" ] && rm -f $O/${tag}_prof_float.ncu-rep
 ls -la $O | grep ${tag}_
