@@ -448,6 +448,135 @@ resample_down_kernel(const ResampleLaunch p) {
   for (int i = lane; i < 64; i += 32) ghist[i] = (int16_t)E[i];
 }
 
+// 640 -> 480 on a REGULAR schedule.  The ratio is 4/3: output n starts its window at E[32 + floor(4 n / 3)]
+// and uses table rows off(n mod 3) = 0, 10, 21 (and the row after) for as long as the reference's running
+// double stays within 1/96 sample of the exact position -- from a stream's second block on and for years
+// (the double of 4/3 is rounded up: the drift is +8e-11 samples per frame; band_host_init.h replays it and
+// the host checks every launch's schedule, so the general kernel above takes whatever is not regular: the
+// priming frames of a new stream).  Regular positions turn the general kernel's 7 instructions per tap
+// (three shared-memory loads, two products, two sums) into 2:
+//   * lane L owns the 15 consecutive outputs n = 15 L + t.  Their windows lie inside the 50 samples
+//     E[32 + 20 L ...], loaded once per frame into registers (13 conflict-free 16-byte loads);
+//   * n mod 3 = t mod 3, so at every unrolled tap all lanes use the same two table rows: the (k1, k2) pairs
+//     sit in the constant bank and are an operand of the multiply, no load at all;
+//   * the sums over k1 and k2 advance together as one packed pair: FFMA2 (product, opaque to contraction:
+//     ns_warp.cuh vmul_o) + FADD2 per tap for both.
+// Every accumulator sees the reference's operations in the reference's order (sinc_resampler_sse.cc:20-57),
+// so the int16 output is bit-identical to the general kernel's.
+__constant__ float2 c_down_pairs[3][32];   // [n mod 3][tap] = (row off, row off + 1), off = 0, 10, 21
+constexpr int kDownRegularRows[3] = {0, 10, 21};
+constexpr int kDownRegularEpos = 32;
+constexpr size_t kResampleDownRegSmemBytes = sizeof(float) * kResampleWarpsPerCta * (64 + 640 + 240);
+
+__global__ void __launch_bounds__(kResampleWarpsPerCta * 32, 4)
+resample_down_regular_kernel(const ResampleLaunch p) {
+  constexpr int SRC = 640, DST = 480, NOUT = 15;
+  extern __shared__ float4 rs_smem4[];
+  float* smem = reinterpret_cast<float*>(rs_smem4);
+  const int lane = lane_id(), warp = (int)(threadIdx.x >> 5);
+  const int lidx = (int)blockIdx.x * kResampleWarpsPerCta + warp;
+  if (lidx >= p.n_streams) return;
+  const int sidx = p.stream_index ? p.stream_index[lidx] : lidx;
+  float* E = smem + warp * (64 + SRC + 240);
+  uint32_t* O = reinterpret_cast<uint32_t*>(E + 64 + SRC);   // the frame's 480 outputs, for coalesced stores
+
+  int32_t* gst = p.state + (size_t)p.slots[sidx] * kBandStateWords;
+  int16_t* ghist = reinterpret_cast<int16_t*>(gst + kBandOffSynHist);
+  for (int i = lane; i < 64; i += 32) E[i] = (float)ghist[i];
+  const int16_t* in = p.in + (size_t)sidx * p.in_stream_stride;
+  int16_t* outp = p.out + (size_t)sidx * p.out_stream_stride;
+  constexpr int kW = SRC / 64;   // 10 words per lane
+  uint32_t nxt[kW];
+  auto fetch = [&](int f) {
+    if (f < p.frames) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)f * p.in_frame_stride);
+#pragma unroll
+      for (int u = 0; u < kW; ++u) nxt[u] = src[lane + 32 * u];
+    }
+  };
+  fetch(0);
+  for (int f = 0; f < p.frames; ++f) {
+#pragma unroll
+    for (int u = 0; u < kW; ++u) {
+      const int wd = lane + 32 * u;
+      *reinterpret_cast<float2*>(E + 64 + 2 * wd) =
+          make_float2((float)(int16_t)(nxt[u] & 0xffffu), (float)(int16_t)(nxt[u] >> 16));
+    }
+    const int32_t* sp = p.schedule + ((size_t)f * DST + NOUT * lane) * 3;
+    fetch(f + 1);
+    __syncwarp();
+    float x[52];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(E + kDownRegularEpos + 20 * lane + 4 * j);
+      x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+    }
+    // phase by phase: the five outputs t = ph, ph + 3, ... share their table rows, so each (k1, k2) pair
+    // is fetched from the constant bank once per frame
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      float2 acc[5][4], w[5];   // w: (1 - factor, factor) of the phase's outputs (the schedule is shared by the group: L1 hits)
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        w[u] = make_float2(__int_as_float(sp[3 * (ph + 3 * u) + 2]), __int_as_float(sp[3 * (ph + 3 * u) + 1]));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[u][q] = make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 k12 = c_down_pairs[ph][i + q];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int rel = (4 * (ph + 3 * u)) / 3;
+            acc[u][q] = vadd(acc[u][q], vmul_o(make_float2(x[rel + i + q], x[rel + i + q]), k12));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int t = ph + 3 * u;
+        // sinc_resampler_sse.cc:42-54: sums1 * (1 - factor) + sums2 * factor per SSE lane, then (s0 + s2) + (s1 + s3)
+        float tq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 pr = vmul(acc[u][q], w[u]);
+          tq[q] = pr.x + pr.y;
+        }
+        const uint32_t v = (uint32_t)band_round_s16((tq[0] + tq[2]) + (tq[1] + tq[3])) & 0xffffu;
+        // output n = 15 lane + t: int16 pairs straddle lanes when lane is odd, so go through 16-bit stores
+        reinterpret_cast<uint16_t*>(O)[NOUT * lane + t] = (uint16_t)v;
+      }
+    }
+    __syncwarp();
+    {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(outp + (size_t)f * p.out_frame_stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int wd = lane + 32 * u;
+        if (wd < DST / 2) dst[wd] = O[wd];
+      }
+    }
+    // history: last 64 input samples
+    const float h0 = E[SRC + lane], h1 = E[SRC + 32 + lane];
+    __syncwarp();
+    E[lane] = h0;
+    E[32 + lane] = h1;
+    __syncwarp();
+  }
+  for (int i = lane; i < 64; i += 32) ghist[i] = (int16_t)E[i];
+}
+
+// Is frame f of a 640 -> 480 schedule (480 x 3 words, band_host_init.h) regular in the above sense?
+inline bool band_down_frame_regular(const int32_t* sched) {
+  for (int n = 0; n < 480; ++n) {
+    const int32_t w0 = sched[3 * n];
+    if ((w0 & 0xff) != kDownRegularRows[n % 3] || (w0 >> 8) != kDownRegularEpos + (4 * n) / 3) return false;
+  }
+  return true;
+}
+
 // ---- launch helpers (host) -------------------------------------------------------
 // The band path is a chain of stages around the suppressor, each a kernel that walks the frames
 // of its streams serially (filter / resampler state in registers).  Stage s of frames [f0, f0+nf)
@@ -464,7 +593,8 @@ struct BandLaunch {
   const float* kernel_down;
   // 48 kHz merge: the 640 -> 480 resampler runs once per group of streams that share a
   // position schedule (normally one group = the whole batch)
-  struct DownGroup { const int32_t* schedule; const int* stream_index; int count; };
+  // regular[f]: frame f of the schedule can take the fast kernel (band_down_frame_regular), host memory
+  struct DownGroup { const int32_t* schedule; const int* stream_index; int count; const uint8_t* regular; };
   std::vector<DownGroup> down_groups;
   const int16_t* full_in;     // full-band PCM [stream][frame][fs/100]
   long long full_in_stride;
@@ -594,8 +724,13 @@ inline int LaunchBandStage(int nb, const BandLaunch& b, int stage, int f0, int n
         r.stream_index = g.stream_index; r.in = s64; r.out = fout;
         r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_out_stride; r.out_frame_stride = 480;
         r.n_streams = g.count; r.frames = nf;
-        resample_down_kernel<<<(g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta,
-                                 kResampleWarpsPerCta * 32, kResampleSmemBytes, st>>>(r);
+        bool regular = g.regular != nullptr;
+        for (int f = f0; regular && f < f0 + nf; ++f) regular = g.regular[f] != 0;
+        const int grid = (g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta;
+        if (regular)
+          resample_down_regular_kernel<<<grid, kResampleWarpsPerCta * 32, kResampleDownRegSmemBytes, st>>>(r);
+        else
+          resample_down_kernel<<<grid, kResampleWarpsPerCta * 32, kResampleSmemBytes, st>>>(r);
         ++*launches;
       }
       break;

@@ -90,6 +90,7 @@ struct DeviceCtx {
   NsxTables* d_nsx_tables = nullptr;
   float* d_sinc_up = nullptr;     // 33 x 32 taps, 480 -> 640
   float* d_sinc_down = nullptr;   // 33 x 32 taps, 640 -> 480
+  std::vector<std::vector<uint8_t>> down_regular;   // scratch of RunBandBlock (48 kHz merge)
   SlabPool f_state, f_hist, x_state, b_state;  // float state, float histograms, fixed state, band-split state
   void* d_template = nullptr;   // scratch for Init templates
   size_t template_bytes = 0;
@@ -306,6 +307,14 @@ int DeviceReady(int dev, DeviceCtx** out) {
       band_make_sinc_kernel(640.0 / 480.0, k.data());
       CU_OK(cudaMalloc(&d.d_sinc_down, sizeof(float) * k.size()));
       CU_OK(cudaMemcpy(d.d_sinc_down, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice));
+      {
+        // the rows a regular 640 -> 480 schedule uses, as (row, row + 1) pairs per tap (band_kernels.cuh)
+        float2 pairs[3][32];
+        for (int ph = 0; ph < 3; ++ph)
+          for (int i = 0; i < 32; ++i)
+            pairs[ph][i] = make_float2(k[(size_t)kDownRegularRows[ph] * 32 + i], k[(size_t)(kDownRegularRows[ph] + 1) * 32 + i]);
+        CU_OK(cudaMemcpyToSymbol(c_down_pairs, pairs, sizeof(pairs)));
+      }
     }
     d.f_state.slab_bytes = sizeof(uint32_t) * kNsfStateWords;
     d.f_hist.slab_bytes = sizeof(uint32_t) * kNsfHistWords;
@@ -773,6 +782,8 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
     const size_t words = (size_t)frames * 480 * 3;
     std::vector<std::vector<int32_t>> scheds;
     std::vector<std::vector<int>> members;
+    std::vector<std::vector<uint8_t>>& regular = d.down_regular;   // per schedule, per frame: fast-kernel eligible
+    regular.clear();
     std::vector<std::pair<double, std::pair<int, double>>> seen;   // start -> (schedule, end)
     for (int i = 0; i < n; ++i) {
       const double v0 = hs[i]->down_vsi;
@@ -789,6 +800,8 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
           if (memcmp(scheds[g].data(), sc.data(), words * sizeof(int32_t)) == 0) { gi = (int)g; break; }
         if (gi < 0) {
           gi = (int)scheds.size();
+          regular.emplace_back((size_t)frames);
+          for (int f = 0; f < frames; ++f) regular.back()[f] = band_down_frame_regular(sc.data() + (size_t)f * 480 * 3);
           scheds.push_back(std::move(sc));
           members.emplace_back();
         }
@@ -814,6 +827,7 @@ int RunBandBlock(DeviceCtx& d, uint32_t magic, std::vector<Handle*>& hs, const i
       dg.schedule = d.d_down_sched + g * words;
       dg.count = (int)members[g].size();
       dg.stream_index = nullptr;
+      dg.regular = regular[g].data();
       if (scheds.size() > 1) {
         CU_OK(cudaMemcpyAsync(d_idx + idx_off, members[g].data(), sizeof(int) * members[g].size(),
                               cudaMemcpyHostToDevice, st));
