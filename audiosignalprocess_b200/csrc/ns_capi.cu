@@ -1588,6 +1588,32 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
       if (nsb_sqrtf(xs) != 0.f || nsb_sqrtf(0.f) != 0.f) ++mism;
       if (nsb_sqrtf_p1(xs) != 1.f || nsb_sqrtf_p1(0.f) != 1.f) ++mism;
     }
+    {
+      // packed fp32 (f32x2) forms of ns_warp.cuh against scalar arithmetic: a product that feeds a sum must not
+      // be contracted into an FMA (ptxas does that to mul.f32x2 + add.f32x2 whatever --fmad says), the swapped /
+      // negated second operands of FADD2 must mean what the source says, and a logarithm of either half of a
+      // packed result must be that of the scalar (nvcc once dropped the exponent shift for one half)
+      const float2 pa = make_float2(a, b), pb = make_float2(__uint_as_float((h2 & 0x807fffffu) | 0x3f000000u), a * 0.37f);
+      const float2 pc = make_float2(b * 1.7f, __uint_as_float((h1 & 0x807fffffu) | 0x3f800000u));
+      const float2 pd = make_float2(-b, 3.f * a);
+      auto same2 = [](float2 g, float wx, float wy) { return __float_as_uint(g.x) == __float_as_uint(wx) && __float_as_uint(g.y) == __float_as_uint(wy); };
+      if (!same2(vmadd(pa, pb, pc), __fadd_rn(__fmul_rn(pa.x, pb.x), pc.x), __fadd_rn(__fmul_rn(pa.y, pb.y), pc.y))) ++mism;
+      if (!same2(vmmadd(pa, pb, pc, pd), __fadd_rn(__fmul_rn(pa.x, pb.x), __fmul_rn(pc.x, pd.x)),
+                 __fadd_rn(__fmul_rn(pa.y, pb.y), __fmul_rn(pc.y, pd.y)))) ++mism;
+      if (!same2(cmul(pb, pc), __fsub_rn(__fmul_rn(pb.x, pc.x), __fmul_rn(pb.y, pc.y)),
+                 __fadd_rn(__fmul_rn(pb.x, pc.y), __fmul_rn(pb.y, pc.x)))) ++mism;
+      if (!same2(cmul_conj(pb, pc), __fadd_rn(__fmul_rn(pb.x, pc.x), __fmul_rn(pb.y, pc.y)),
+                 __fsub_rn(__fmul_rn(pb.y, pc.x), __fmul_rn(pb.x, pc.y)))) ++mism;
+      if (!same2(cadd_i(pa, pc), __fsub_rn(pa.x, pc.y), __fadd_rn(pa.y, pc.x))) ++mism;
+      if (!same2(csub_i(pa, pc), __fadd_rn(pa.x, pc.y), __fsub_rn(pa.y, pc.x))) ++mism;
+      if (!same2(vfdiv(pa, make_float2(b, pc.y)), fdiv(pa.x, b), fdiv(pa.y, pc.y))) ++mism;
+      const float2 sq = vmmadd(pb, pb, pc, pc);
+      const float2 mg = vsqrt_p1(sq);
+      if (!same2(mg, nsb_sqrtf_p1(__fadd_rn(__fmul_rn(pb.x, pb.x), __fmul_rn(pc.x, pc.x))),
+                 nsb_sqrtf_p1(__fadd_rn(__fmul_rn(pb.y, pb.y), __fmul_rn(pc.y, pc.y))))) ++mism;
+      const float2 lg = vlog_rn(vadd(mg, make_float2(fabsf(b), 0.25f)));
+      if (!same2(lg, nsb_log_rn(__fadd_rn(mg.x, fabsf(b))), nsb_log_rn(__fadd_rn(mg.y, 0.25f)))) ++mism;
+    }
     const float c = (float)(h1 % 401u);   // small integers as in counters
     selftest_div(fdiv(c, (float)(h2 % 200u + 1u)), __fdiv_rn(c, (float)(h2 % 200u + 1u)), mism, ulp1, ndiv);
     int32_t v = (int32_t)h2, root = 0;

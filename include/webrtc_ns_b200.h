@@ -164,7 +164,8 @@ const char* WebRtcNsB200_LastError(void);
 /* Kernels launched by this library since load (for bench.py's gpu_launches). */
 uint64_t WebRtcNsB200_KernelLaunches(void);
 /* Device self-test of the kernels' arithmetic shortcuts against their exact definitions over
- * n_cases operands: logf, sqrtf, int16 rounding and the floor square root must be identical;
+ * n_cases operands: logf, sqrtf, int16 rounding, the floor square root and the packed (f32x2) forms
+ * of multiply-add, complex multiply, division and square root must be identical to the scalar ones;
  * the branch-free division must equal IEEE division except for at most 2 per million quotients
  * that may be one ulp off; the tracker's logarithm must be the double-precision logarithm rounded
  * to float, likewise the exponential and the sigmoid map built on tanh (never more than an ulp off, at
