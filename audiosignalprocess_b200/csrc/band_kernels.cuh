@@ -285,6 +285,8 @@ constexpr size_t kResampleUpSmemBytes = sizeof(float) * (kResampleWarpsPerCta * 
 // are ever used and the interpolation factor is exactly 0.  The four rows live in constant
 // memory: every tap is an FMUL with a constant-bank operand, no load at all.
 __constant__ float c_up_rows[4][32];
+// the same rows as pairs of adjacent taps: [0][row][k] = (c[2k], c[2k+1]), [1][row][k] = (c[2k+1], c[2k+2]) (k < 15)
+__constant__ float2 c_up_pairs[2][4][16];
 
 // Lane owns the 20 consecutive outputs n = 20 lane + t: their windows start at
 // E[15 lane + ((126 + 3t) >> 2)], so 46 input samples held in registers serve all 20 outputs
@@ -326,24 +328,45 @@ resample_up_kernel(const ResampleLaunch p) {
     float x[46];
 #pragma unroll
     for (int j = 0; j < 46; ++j) x[j] = E[15 * lane + 31 + j];
-    uint32_t packed[10];
+    uint32_t packed[10] = {};
+    // The four SSE-lane sums a0..a3 (taps i = q mod 4) advance two at a time as packed pairs of ADJACENT taps:
+    // where the window starts at an even register the pairs are (a0, a1) and (a2, a3); where it starts at an
+    // odd one they are (a1, a2) and (a3 at tap i, a0 at tap i + 4), with a0's first and a3's last term scalar
+    // -- either way every sum sees its terms in the reference's order.  Tap pairs come from the constant
+    // bank (c_up_pairs: both alignments); outputs are visited grouped by (table row, alignment) so that a pair
+    // fetched once serves the two or three outputs that use it.
 #pragma unroll
-    for (int t = 0; t < 20; ++t) {
-      const int rel = ((126 + 3 * t) >> 2) - 31;        // window start relative to x[0]
-      const int row = (126 + 3 * t) & 3;                // table row 8 * row = c_up_rows[row]
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int grp = 0; grp < 8; ++grp) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        a0 += x[rel + i] * c_up_rows[row][i];
-        a1 += x[rel + i + 1] * c_up_rows[row][i + 1];
-        a2 += x[rel + i + 2] * c_up_rows[row][i + 2];
-        a3 += x[rel + i + 3] * c_up_rows[row][i + 3];
+      for (int t = 0; t < 20; ++t) {
+        const int rel = ((126 + 3 * t) >> 2) - 31;        // window start relative to x[0]
+        const int row = (126 + 3 * t) & 3;                // table row 8 * row = c_up_rows[row]
+        if (((rel & 1) * 4 + row) != grp) continue;
+        float a0, a1, a2, a3;
+        if ((rel & 1) == 0) {
+          float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            s01 = vadd(s01, vmul_o(make_float2(x[rel + i], x[rel + i + 1]), c_up_pairs[0][row][i / 2]));
+            s23 = vadd(s23, vmul_o(make_float2(x[rel + i + 2], x[rel + i + 3]), c_up_pairs[0][row][i / 2 + 1]));
+          }
+          a0 = s01.x; a1 = s01.y; a2 = s23.x; a3 = s23.y;
+        } else {
+          float2 s12 = make_float2(0.f, 0.f), s30 = make_float2(0.f, 0.f + x[rel] * c_up_rows[row][0]);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            s12 = vadd(s12, vmul_o(make_float2(x[rel + i + 1], x[rel + i + 2]), c_up_pairs[1][row][i / 2]));
+            if (i < 28) s30 = vadd(s30, vmul_o(make_float2(x[rel + i + 3], x[rel + i + 4]), c_up_pairs[1][row][i / 2 + 1]));
+          }
+          a0 = s30.y; a1 = s12.x; a2 = s12.y;
+          a3 = s30.x + x[rel + 31] * c_up_rows[row][31];
+        }
+        // sinc_resampler_sse.cc:42-54 with interpolation factor 0: a*1 + b*0 == a for the finite
+        // sums b of the second kernel (up to the sign of zero, gone after rounding)
+        const int v = band_round_s16((a0 + a2) + (a1 + a3));
+        if (t & 1) packed[t >> 1] = (packed[t >> 1] & 0xffffu) | ((uint32_t)v << 16);
+        else packed[t >> 1] = (packed[t >> 1] & 0xffff0000u) | ((uint32_t)v & 0xffffu);
       }
-      // sinc_resampler_sse.cc:42-54 with interpolation factor 0: a*1 + b*0 == a for the finite
-      // sums b of the second kernel (up to the sign of zero, gone after rounding)
-      const int v = band_round_s16((a0 + a2) + (a1 + a3));
-      if (t & 1) packed[t >> 1] |= (uint32_t)v << 16;
-      else packed[t >> 1] = (uint32_t)v & 0xffffu;
     }
     uint2* dst = reinterpret_cast<uint2*>(out + (size_t)f * p.out_frame_stride + 20 * lane);
 #pragma unroll

@@ -303,6 +303,13 @@ int DeviceReady(int dev, DeviceCtx** out) {
         const int which[4] = {0, 8, 16, 24};
         for (int r = 0; r < 4; ++r) memcpy(rows[r], k.data() + which[r] * 32, sizeof(rows[r]));
         CU_OK(cudaMemcpyToSymbol(c_up_rows, rows, sizeof(rows)));
+        float2 pairs[2][4][16];
+        for (int r = 0; r < 4; ++r)
+          for (int kk = 0; kk < 16; ++kk) {
+            pairs[0][r][kk] = make_float2(rows[r][2 * kk], rows[r][2 * kk + 1]);
+            pairs[1][r][kk] = kk < 15 ? make_float2(rows[r][2 * kk + 1], rows[r][2 * kk + 2]) : make_float2(0.f, 0.f);
+          }
+        CU_OK(cudaMemcpyToSymbol(c_up_pairs, pairs, sizeof(pairs)));
       }
       band_make_sinc_kernel(640.0 / 480.0, k.data());
       CU_OK(cudaMalloc(&d.d_sinc_down, sizeof(float) * k.size()));
