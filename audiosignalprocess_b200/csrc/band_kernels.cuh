@@ -21,6 +21,7 @@
 #define AUDIOSIGNALPROCESS_B200_BAND_KERNELS_CUH_
 
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -747,7 +748,9 @@ inline int LaunchBandStage(int nb, const BandLaunch& b, int stage, int f0, int n
         r.stream_index = g.stream_index; r.in = s64; r.out = fout;
         r.in_stream_stride = ss; r.in_frame_stride = 640; r.out_stream_stride = b.full_out_stride; r.out_frame_stride = 480;
         r.n_streams = g.count; r.frames = nf;
-        bool regular = g.regular != nullptr;
+        // NSB200_BAND_GENERAL_DOWN=1 keeps the general kernel (test hook: both must give the same bits)
+        static const bool force_general = getenv("NSB200_BAND_GENERAL_DOWN") != nullptr;
+        bool regular = g.regular != nullptr && !force_general;
         for (int f = f0; regular && f < f0 + nf; ++f) regular = g.regular[f] != 0;
         const int grid = (g.count + kResampleWarpsPerCta - 1) / kResampleWarpsPerCta;
         if (regular)

@@ -146,3 +146,39 @@ def test_frame_chunk_pipeline_bit_exact(nslib, reflib, fs, chunk, monkeypatch):
             assert np.array_equal(ob[i], reflib.nsx(fs, mode, x[i][:rest * fl])), "fresh stream %d" % i
     for i in range(n):
         lib.WebRtcNsx_Free(hs[i])
+
+
+def test_48k_regular_and_general_resampler_kernels_agree(reflib):
+    """From a stream's second block on the 640 -> 480 merge runs `resample_down_regular_kernel` (positions on
+    the 4/3 lattice, taps from the constant bank, packed sums); NSB200_BAND_GENERAL_DOWN=1 keeps the general
+    kernel.  Same int16 bits either way, and both equal the reference (a fresh process per setting: the
+    library reads the hook once)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import audiosignalprocess_b200 as pkg\n"
+        "from conftest import RefLib\n"
+        "n, fs, frames = 6, 48000, 260\n"
+        "x = pkg.synth_pcm_host(n, fs, frames * 480)\n"
+        "b = pkg.NsBatch(n, fs, 2, fixed=True)\n"
+        "out = np.concatenate([b.process(np.ascontiguousarray(x[:, f0 * 480:(f0 + 52) * 480])) for f0 in range(0, frames, 52)], axis=1)\n"
+        "ref = RefLib(%r)\n"
+        "ok = all(np.array_equal(ref.nsx(fs, 2, x[s]), out[s]) for s in range(n))\n"
+        "print('RESULT', hashlib.sha256(out.tobytes()).hexdigest(), int(ok))\n"
+    ) % (root, os.path.join(root, "tests"), os.path.join(root, "oracle", "_ref", "libns_ref.so"))
+    got = []
+    for force in (False, True):
+        env = dict(os.environ)
+        env.pop("NSB200_BAND_GENERAL_DOWN", None)
+        if force:
+            env["NSB200_BAND_GENERAL_DOWN"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
+        assert r.returncode == 0 and line, r.stdout + r.stderr
+        got.append(line[0].split()[1:])
+    assert got[0][1] == "1" and got[1][1] == "1", "output differs from the reference: %r" % got
+    assert got[0][0] == got[1][0]
