@@ -31,6 +31,17 @@
 namespace nsb200 {
 
 NSB_DEV int band_sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+// the low (sel 0x9910) or high (sel 0xBB32) int16 of a word, sign-extended: one byte permute whose selector
+// replicates the sign of the half's upper byte
+NSB_DEV int band_half_s16(uint32_t w, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+  int r;   // (prmt directly: __byte_perm does not promise the sign-replication bit of the selector)
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
+  return r;
+#else
+  return sel == 0x9910u ? (int)(int16_t)(w & 0xffffu) : (int)(int16_t)(w >> 16);
+#endif
+}
 NSB_DEV int band_round_s16(float v) {  // FloatS16ToS16, common_audio/include/audio_util.h:41-49
   if (v > 0.f) return v >= 32766.5f ? 32767 : (int)(v + 0.5f);
   return v <= -32767.5f ? -32768 : (int)(v - 0.5f);
@@ -100,6 +111,10 @@ __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p)
   const int inst = live ? unit % p.instances : 0;
   const int sidx = live ? unit / p.instances : 0;
   const int c0 = chain == 0 ? 6418 : 21333, c1 = chain == 0 ? 36982 : 49062, c2 = chain == 0 ? 57261 : 63010;
+  // per-thread constants that replace selects in the sample loop: which int16 of a word this chain filters
+  // (byte selector with sign replication), and the sign of its own output in low = f1 + f2, high = f1 - f2
+  const uint32_t half_sel = chain == 0 ? 0xBB32u : 0x9910u;
+  const int own_sign = chain == 0 ? 1 : -1;
   int st[6] = {0, 0, 0, 0, 0, 0};
   int32_t* gst = nullptr;
   if (live) {
@@ -145,12 +160,11 @@ __global__ void __launch_bounds__(128) qmf_analysis_kernel(const QmfAnaLaunch p)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         // chain 0 filters in[2i+1], chain 1 filters in[2i]; both in Q10
-        const int x = (chain == 0 ? (int)(int16_t)(w[k] >> 16) : (int)(int16_t)(w[k] & 0xffffu)) * 1024;
+        const int x = band_half_s16(w[k], half_sel) * 1024;
         const int y = band_allpass3(x, st, c0, c1, c2);
         const int other = __shfl_xor_sync(kFullMask, y, 1);
-        const int f1 = chain == 0 ? y : other, f2 = chain == 0 ? other : y;
-        // chain 0 emits the low band, chain 1 the high band (:156-163)
-        const int v = chain == 0 ? band_sat16((f1 + f2 + 1024) >> 11) : band_sat16((f1 - f2 + 1024) >> 11);
+        // chain 0 emits the low band (f1 + f2 = y + other), chain 1 the high band (f1 - f2 = other - y) (:156-163)
+        const int v = band_sat16((other + (y * own_sign + 1024)) >> 11);
         if (k & 1) packed[k >> 1] |= (uint32_t)v << 16;
         else packed[k >> 1] = (uint32_t)v & 0xffffu;
       }
@@ -189,6 +203,8 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
   const int sidx = live ? unit / p.instances : 0;
   // chain 0: state1 with kAllPassFilter2 on (low+high); chain 1: state2 with kAllPassFilter1 on (low-high)
   const int c0 = chain == 0 ? 21333 : 6418, c1 = chain == 0 ? 49062 : 36982, c2 = chain == 0 ? 63010 : 57261;
+  const int high_sign = chain == 0 ? 1 : -1;   // input low + high (chain 0) or low - high (chain 1)
+  const uint32_t pair_sel = chain == 0 ? 0x1054u : 0x5410u;   // byte selector of (even, odd) from (own, other)
   int st[6] = {0, 0, 0, 0, 0, 0};
   int32_t* gst = nullptr;
   if (live) {
@@ -229,13 +245,17 @@ __global__ void __launch_bounds__(128) qmf_synthesis_kernel(const QmfSynLaunch p
       for (int k = 0; k < 8; ++k) {
         const int lv = (int)(int16_t)((k & 1) ? (l[k >> 1] >> 16) : (l[k >> 1] & 0xffffu));
         const int hv = (int)(int16_t)((k & 1) ? (h[k >> 1] >> 16) : (h[k >> 1] & 0xffffu));
-        const int x = (chain == 0 ? lv + hv : lv - hv) * 1024;
+        const int x = (hv * high_sign + lv) * 1024;
         const int y = band_allpass3(x, st, c0, c1, c2);
         const int v = band_sat16((y + 512) >> 10);
         const int other = __shfl_xor_sync(kFullMask, v, 1);
-        // out[2i] = chain 1 (filter2), out[2i+1] = chain 0 (filter1)
+        // out[2i] = chain 1 (filter2), out[2i+1] = chain 0 (filter1): chain 0 packs (other, own), chain 1 (own, other)
+#ifdef __CUDA_ARCH__
+        ow[k] = __byte_perm((uint32_t)v, (uint32_t)other, pair_sel);
+#else
         const int even = chain == 0 ? other : v, odd = chain == 0 ? v : other;
         ow[k] = ((uint32_t)even & 0xffffu) | ((uint32_t)odd << 16);
+#endif
       }
       // the pair of lanes holds the same 8 words: chain 0 stores the first half
       if (out_base) {
@@ -492,7 +512,10 @@ constexpr int kDownRegularRows[3] = {0, 10, 21};
 constexpr int kDownRegularEpos = 32;
 constexpr size_t kResampleDownRegSmemBytes = sizeof(float) * kResampleWarpsPerCta * (64 + 640 + 240);
 
-__global__ void __launch_bounds__(kResampleWarpsPerCta * 32, 4)
+#ifndef NSB_DOWN_MIN_CTAS
+#define NSB_DOWN_MIN_CTAS 3   // 168 registers: the constant-bank tap pairs stay in registers across a phase (4: 127 registers, +170 MOV/LDC per frame, 3 % slower step)
+#endif
+__global__ void __launch_bounds__(kResampleWarpsPerCta * 32, NSB_DOWN_MIN_CTAS)
 resample_down_regular_kernel(const ResampleLaunch p) {
   constexpr int SRC = 640, DST = 480, NOUT = 15;
   extern __shared__ float4 rs_smem4[];
