@@ -563,6 +563,11 @@ nsx_process_kernel(const NsxLaunch p) {
           latch[s] = cnt[s] >= 200;
           Hw[kX_counter + s] = (latch[s] ? 0 : cnt[s]) + 1;
         }
+        // loop-invariant over the bins: the density increment and the start-up step
+        int bb[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) bb[s] = fx_s16(fx_mul_rsft_round(21845, cdiv[s], 15));
+        const int dsmall = block_index < 200 ? 1024 : 5120;
         // which estimator (if any) is latched into noiseEstQuantile this frame
         int sel = -1;
         if (block_index >= 200) {
@@ -582,35 +587,27 @@ nsx_process_kernel(const NsxLaunch p) {
           int lq[3] = {fx_lo(a.x), fx_hi(a.x), fx_lo(a.y)};
           int dn[3] = {fx_hi(a.y), fx_lo(a.z), fx_hi(a.z)};
           quant[j] = fx_lo(a.w);
-          int lmagn = logval;
-          if (magn[j]) {
-            const int l2 = nsx_log2_q8(magn[j], s_logf);
-            lmagn = fx_s16(fx_s16((l2 * 22713) >> 15) + logval);
-          }
+          // Branch-free: every data-dependent `if` of the reference's loop body (nsx_core.c:361-430) is a select
+          // here, so that the 15 tracker updates of a lane form one block the scheduler can interleave.
+          // fx_norm_u32(0) = 0 and the table entry of a zero fraction is 0, so the logarithm of magn = 0 is
+          // computed harmlessly and discarded.
+          const int l2 = nsx_log2_q8(magn[j], s_logf);
+          const int lmagn = magn[j] ? fx_s16(fx_s16((l2 * 22713) >> 15) + logval) : logval;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            int delta;
-            if (dn[s] > 512) {
-              delta = fx_s16(2621440 >> (14 - fx_norm_w16(dn[s])));
-            } else {
-              delta = block_index < 200 ? 1024 : 5120;
-            }
-            int t16 = fx_s16((delta * cdiv[s]) >> 14);
-            if (lmagn > lq[s]) {
-              t16 = fx_s16(t16 + 2);
-              lq[s] = fx_s16(lq[s] + t16 / 4);
-            } else {
-              t16 = fx_s16(t16 + 1);
-              const int t2 = fx_s16((fx_s16(t16 / 2) * 3) >> 1);
-              lq[s] = fx_s16(lq[s] - t2);
-              if (lq[s] < logval) lq[s] = logval;
-            }
+            // density > 512: delta = FACTOR_Q7 >> (14 - norm16(density)) = 2621440 >> (31 - clz(density))
+            const int dv = dn[s] > 513 ? dn[s] : 513;
+            const int delta = dn[s] > 512 ? fx_s16(2621440 >> (31 - __clz(dv))) : dsmall;
+            // delta in [160, 5120] and counter_div in (0, 32767]: 0 <= t16 <= 10240, so the reference's
+            // (int16_t) casts of t16 + 1, t16 + 2 and their halves / quarters (exact shifts) are identities
+            const int t16 = (delta * cdiv[s]) >> 14;
+            const int lq_up = fx_s16(lq[s] + ((t16 + 2) >> 2));
+            const int lq_dn0 = fx_s16(lq[s] - ((((t16 + 1) >> 1) * 3) >> 1));
+            const int lq_dn = lq_dn0 < logval ? logval : lq_dn0;
+            lq[s] = lmagn > lq[s] ? lq_up : lq_dn;
             const int d = fx_s16(lmagn - lq[s]);
-            if ((d >= 0 ? d : -d) < 3) {
-              const int aa = fx_s16(fx_mul_rsft_round(dn[s], cprod[s], 15));
-              const int bb = fx_s16(fx_mul_rsft_round(21845, cdiv[s], 15));
-              dn[s] = fx_s16(aa + bb);
-            }
+            const int aa = fx_s16(fx_mul_rsft_round(dn[s], cprod[s], 15));
+            dn[s] = (d >= 0 ? d : -d) < 3 ? fx_s16(aa + bb[s]) : dn[s];
           }
           lqs[j] = sel == 0 ? lq[0] : (sel == 1 ? lq[1] : lq[2]);
           if (mine && sel >= 0 && lqs[j] > mx) mx = lqs[j];
