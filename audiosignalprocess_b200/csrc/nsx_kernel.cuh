@@ -736,29 +736,23 @@ nsx_process_kernel(const NsxLaunch p) {
         const int nsh = 5 - prev_q_magn + prev_q_noise;
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
-          post_snr[j] = 2048u;
+          // (branch-free: the divisions run on a guarded divisor and the reference's cases select the result,
+          // so that the five slots' division chains interleave)
           unsigned u1 = magn[j] << 6;
           unsigned u2 = post_shifts < 0 ? (noise[j] >> -post_shifts) : (noise[j] << post_shifts);
-          if (u1 > u2) {
-            u1 <<= 11;
-            if (u2 > 0u) {
-              u1 /= u2;
-              post_snr[j] = u1 < sat_max ? u1 : sat_max;
-            } else {
-              post_snr[j] = sat_max;
-            }
+          {
+            const unsigned q = (u1 << 11) / (u2 ? u2 : 1u);
+            const unsigned capped = (u2 && q < sat_max) ? q : sat_max;
+            post_snr[j] = u1 > u2 ? capped : 2048u;
           }
           const unsigned prev_magn = rb[j].w & 0xffffu;
           const unsigned near_est = prev_magn * filter_prev[j];
           u1 = near_est << 3;
           u2 = rb[j].z >> nsh;
-          if (u2 > 0u) {
-            u1 /= u2;
-            if (u1 > sat_max) u1 = sat_max;
-          } else {
-            u1 = sat_max;
+          {
+            const unsigned q = u1 / (u2 ? u2 : 1u);
+            prev_near[j] = (u2 && q < sat_max) ? q : sat_max;
           }
-          prev_near[j] = u1;
           const unsigned prior = prev_near[j] * 2007u + (post_snr[j] - 2048u) * 41u + 512u;
           prior_snr[j] = 2048u + (prior >> 10);
         }
@@ -890,8 +884,7 @@ nsx_process_kernel(const NsxLaunch p) {
           const int nt = fx_norm_u32(post_snr[j]);
           const unsigned num = post_snr[j] << nt;
           const unsigned den = nt > 10 ? (prior_snr[j] << (nt - 11)) : (prior_snr[j] >> (11 - nt));
-          if (den > 0u) bessel -= (int)(num / den);
-          else bessel = 0;
+          bessel = den ? bessel - (int)(num / (den ? den : 1u)) : 0;
           const int zeros = fx_norm_u32(prior_snr[j]);
           int frac32 = (int)(((prior_snr[j] << zeros) & 0x7FFFFFFFu) >> 19);
           int t = (frac32 * frac32 * -43) >> 19;
@@ -973,33 +966,32 @@ nsx_process_kernel(const NsxLaunch p) {
         const int d16 = fx_s16(ind16 - prior_ns);
         prior_ns = fx_s16(prior_ns + fx_s16((1638 * d16) >> 14));
         Hw[kX_priorNonSpeech] = prior_ns;
+        const int n2_prior = fx_norm_w16(16384 - prior_ns);
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
-          nonspeech[j] = 0u;
-          if (prior_ns > 0 && lrt[j] < 65300) {
-            const int e = (lrt[j] * 23637) >> 14;
-            int int_part = fx_s16(e >> 12);
-            if (int_part < -8) int_part = -8;
-            const int frac = fx_s16(e & 0xfff);
-            int t2 = (frac * frac * 44) >> 19;
-            t2 += (frac * 84) >> 7;
-            int inv = fx_shl(1, 8 + int_part) + fx_shift_w32(t2, int_part - 4);
-            const int n1 = fx_norm_w32(inv);
-            const int n2 = fx_norm_w16(16384 - prior_ns);
-            if (n1 + n2 >= 7) {
-              int pp;
-              if (n1 + n2 < 15) {
-                inv >>= 15 - n2 - n1;
-                pp = inv * (16384 - prior_ns);
-                inv = fx_shift_w32(pp, 7 - n1 - n2);
-              } else {
-                pp = inv * (16384 - prior_ns);
-                inv = pp >> 8;
-              }
-              pp = fx_shl(prior_ns, 8);
-              nonspeech[j] = (unsigned)(pp / (prior_ns + inv)) & 0xffffu;
-            }
-          }
+          // nsx_core_c.c:214-258, branch-free.  The reference evaluates this only for priorNonSpeechProb > 0 and
+          // logLrt < 65300; the clamp keeps the shifts of the discarded case in range.  n = n1 + n2 picks one
+          // of the reference's two scalings, which differ only in their shift counts:
+          //   n < 15:  inv >>= 15 - n;  inv = (inv * (16384 - prior)) >> (n - 7)
+          //   n >= 15:                  inv = (inv * (16384 - prior)) >> 8
+          // Both operands of the last division are positive (0 <= prior <= 16384 by construction of the
+          // indicator mean, inv >= 0), so it is an unsigned division.
+          const int lr = lrt[j] < 65299 ? lrt[j] : 65299;
+          const int e = (lr * 23637) >> 14;
+          int int_part = fx_s16(e >> 12);
+          if (int_part < -8) int_part = -8;
+          const int frac = fx_s16(e & 0xfff);
+          int t2 = (frac * frac * 44) >> 19;
+          t2 += (frac * 84) >> 7;
+          int inv = fx_shl(1, 8 + int_part) + fx_shift_w32(t2, int_part - 4);
+          const int nn = fx_norm_w32(inv) + n2_prior;
+          const int pre = 15 - nn > 0 ? 15 - nn : 0;
+          const int post = nn - 7 < 0 ? 0 : (nn - 7 > 8 ? 8 : nn - 7);
+          inv = ((inv >> pre) * (16384 - prior_ns)) >> post;
+          const bool live = prior_ns > 0 && lrt[j] < 65300 && nn >= 7;
+          const unsigned den = live ? (unsigned)(prior_ns + inv) : 1u;
+          const unsigned q = (unsigned)fx_shl(prior_ns, 8) / den;
+          nonspeech[j] = live ? (q & 0xffffu) : 0u;
           rb[j].x = (uint32_t)lrt[j];
         }
       }
@@ -1009,6 +1001,7 @@ nsx_process_kernel(const NsxLaunch p) {
       {
         const int post_shifts = prev_q_noise - q_magn;
         const int nsh = prev_q_magn - q_magn;
+        const int nsh_up = nsh < 0 ? 0 : nsh;
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
           const bool nyq = j == NSLOT - 1;
@@ -1030,37 +1023,27 @@ nsx_process_kernel(const NsxLaunch p) {
           int sign;
           if (prev_noise16 > u2) { sign = -1; u1 = prev_noise16 - u2; }
           else { sign = 1; u1 = u2 - prev_noise16; }
-          unsigned upd = rb[j].z;
-          unsigned u3 = 0;
-          if (u1 && nonspeech[j]) {
-            u3 = u1 * nonspeech[j];
-            u2 = (0x7c000000u & u3) ? (u3 >> 5) * gamma_in : (u3 * gamma_in) >> 5;
-            if (sign > 0) upd += u2;
-            else upd -= u2;
-          }
+          // Branch-free (nsx_core.c:1868-1931).  With |delta| = 0 or nonSpeechProb = 0 the product u3 is 0 and the
+          // update adds nothing, which is what the reference's `if` skips; when the bin's own gamma equals the
+          // incoming one the second estimate IS the first, so the reference's "take the smaller" is a plain
+          // minimum.
+          const unsigned u3 = u1 * nonspeech[j];
+          const bool big = (0x7c000000u & u3) != 0u;
+          u2 = big ? (u3 >> 5) * gamma_in : (u3 * gamma_in) >> 5;
+          unsigned upd = sign > 0 ? rb[j].z + u2 : rb[j].z - u2;
           const unsigned gamma = nonspeech[j] < 205u ? 3u : 26u;
-          if (gamma_in != gamma) {
-            u2 = (0x7c000000u & u3) ? (u3 >> 5) * gamma : (u3 * gamma) >> 5;
-            u1 = sign > 0 ? rb[j].z + u2 : rb[j].z - u2;
-            if (upd > u1) upd = u1;
-          }
+          u2 = big ? (u3 >> 5) * gamma : (u3 * gamma) >> 5;
+          u1 = sign > 0 ? rb[j].z + u2 : rb[j].z - u2;
+          if (upd > u1) upd = u1;
           noise[j] = upd;
           if (mine && upd > max_noise) max_noise = upd;
-          int t2 = fx_shift_w32((int)rb[j].y, -nsh);
-          if (nonspeech[j] > 205u) {
-            int t1;
-            if (nsh < 0) {
-              t1 = (int)magn[j] - t2;
-              t1 *= 13;
-              t1 = (t1 + 128) >> 8;
-            } else {
-              t1 = fx_shl((int)magn[j], nsh) - (int)rb[j].y;
-              t1 *= 13;
-              t1 = (t1 + fx_shl(128, nsh)) >> (8 + nsh);
-            }
-            t2 += t1;
-          }
-          rb[j].y = (uint32_t)t2;
+          // magnitude during pauses (:1933-1945): both Q-domain cases are one expression in shifts that are
+          // uniform over the frame
+          const int t2 = fx_shift_w32((int)rb[j].y, -nsh);
+          int t1 = fx_shl((int)magn[j], nsh_up) - (nsh < 0 ? t2 : (int)rb[j].y);
+          t1 *= 13;
+          t1 = (t1 + fx_shl(128, nsh_up)) >> (8 + nsh_up);
+          rb[j].y = (uint32_t)(nonspeech[j] > 205u ? t2 + t1 : t2);
         }
       }
       max_noise = warp_max_u(max_noise);
@@ -1088,14 +1071,15 @@ nsx_process_kernel(const NsxLaunch p) {
             tm = magn[j] << nsh;
             tn = noise[j];
           }
-          if (tm > tn) {
+          {
+            // (branch-free: computed on the wrapped difference and discarded unless tm > tn)
             unsigned u1 = tm - tn;
             int nn = fx_norm_u32(u1);
             if (nn > 11) nn = 11;
             u1 <<= nn;
             const unsigned u2 = tn >> (11 - nn);
-            if (u2 > 0u) u1 /= u2;
-            cur_snr = u1 < sat_max ? u1 : sat_max;
+            const unsigned q = u2 ? u1 / (u2 ? u2 : 1u) : u1;
+            cur_snr = tm > tn ? (q < sat_max ? q : sat_max) : 0u;
           }
           const unsigned prior = prev_near[j] * 2007u + cur_snr * 41u;
           const unsigned dn = (unsigned)overdrive + ((prior + 8192u) >> 14);
