@@ -85,25 +85,29 @@ NSB_DEV int fx_hi(uint32_t w) { return (int)(int16_t)(w >> 16); }
 // upper half of the sum scaled to put the kept bits at 16..31 (wrap-around included: the bits shifted out are
 // the ones the cast discards).  The inverse transform at shift 2 keeps bit 31, cannot be doubled, and takes
 // the plain form.
-template <bool INV>
-NSB_DEV void fx_butterfly_u(int& ar, int& ai, int& xr, int& xi, int2 w, int shift) {
-  if (!INV) {
+// SH = -1: forward transform; SH = 0, 1, 2: inverse transform at that scaling shift.  The shift is decided per
+// stage from the data (fx_inverse_shift) and is the same for the whole warp, so the stage is compiled once per
+// value and selected by one warp-uniform branch per stage, instead of a branch and run-time scale factors in
+// every butterfly.
+template <int SH>
+NSB_DEV void fx_butterfly_u(int& ar, int& ai, int& xr, int& xi, int2 w) {
+  if (SH < 0) {
     const unsigned qr = (unsigned)(ar * 32768 + 32768), qi = (unsigned)(ai * 32768 + 32768);
     const int mr = w.x * xr + w.y * xi, mi = w.x * xi - w.y * xr;     // p - 1
     xr = (int)(qr - (unsigned)mr) >> 16;
     xi = (int)(qi - (unsigned)mi) >> 16;
     ar = (int)(qr + 1u + (unsigned)mr) >> 16;
     ai = (int)(qi + 1u + (unsigned)mi) >> 16;
-  } else if (shift < 2) {
-    // scaled by 2^(1 - shift): a * 2^(16 - shift) + 2^15 (+ 2^(1 - shift)) +- (wr xr - ws xi) * 2^(1 - shift)
-    const int m = 2 - shift;                                      // 2 or 1
-    const int yr = xr * m, yi = xi * m;
+  } else if (SH < 2) {
+    // scaled by m = 2^(1 - shift): a * 2^(16 - shift) + 2^15 (+ m) +- m (wr xr - ws xi)   (wrap-around ring
+    // arithmetic: the factor m moves freely between the operands)
+    constexpr int m = 2 - SH;                                     // 2 or 1
     const unsigned qr = (unsigned)(ar * (32768 * m) + 32768), qi = (unsigned)(ai * (32768 * m) + 32768);
-    const int mr = w.x * yr - w.y * yi, mi = w.x * yi + w.y * yr;
-    xr = (int)(qr - (unsigned)mr) >> 16;
-    xi = (int)(qi - (unsigned)mi) >> 16;
-    ar = (int)(qr + (unsigned)m + (unsigned)mr) >> 16;
-    ai = (int)(qi + (unsigned)m + (unsigned)mi) >> 16;
+    const int br = w.x * xr - w.y * xi, bi = w.x * xi + w.y * xr;
+    xr = (int)(qr - (unsigned)(br * m)) >> 16;
+    xi = (int)(qi - (unsigned)(bi * m)) >> 16;
+    ar = (int)(qr + (unsigned)m + (unsigned)(br * m)) >> 16;
+    ai = (int)(qi + (unsigned)m + (unsigned)(bi * m)) >> 16;
   } else {
     const int tr = (w.x * xr - w.y * xi + 1) >> 1, ti = (w.x * xi + w.y * xr + 1) >> 1;
     const int qr = ar * 16384 + 32768, qi = ai * 16384 + 32768;
@@ -135,27 +139,36 @@ NSB_DEV int fx_inverse_shift(const int (&re)[8], const int (&im)[8], bool act) {
 // Runs NST stages starting at stage S0 on the lane's 8 points; the butterfly partners differ in local bit
 // BIT0 + t.  twi(s, r) = index of the butterfly's twiddle in the regrouped table.  Returns the accumulated
 // inverse scale.
-template <bool INV, int S0, int NST, int BIT0, typename TwFn>
-NSB_DEV int fx_local_stages_u(int (&re)[8], int (&im)[8], const int2* tw, bool act, TwFn twi) {
-  int scale = 0;
+template <int SH, int STAGE, int BITPOS, typename TwFn>
+NSB_DEV void fx_stage_u(int (&re)[8], int (&im)[8], const int2* tw, TwFn twi) {
 #pragma unroll
-  for (int t = 0; t < NST; ++t) {
-    int shift = 0;
-    if (INV) {
-      shift = fx_inverse_shift(re, im, act);
-      scale += shift;
-    }
-    if (act) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (!((r >> (BIT0 + t)) & 1)) {
-          const int r2 = r | (1 << (BIT0 + t));
-          fx_butterfly_u<INV>(re[r], im[r], re[r2], im[r2], tw[twi(S0 + t, r)], shift);
-        }
-      }
+  for (int r = 0; r < 8; ++r) {
+    if (!((r >> BITPOS) & 1)) {
+      const int r2 = r | (1 << BITPOS);
+      fx_butterfly_u<SH>(re[r], im[r], re[r2], im[r2], tw[twi(STAGE, r)]);
     }
   }
+}
+template <bool INV, int S0, int NST, int BIT0, int T, typename TwFn>
+NSB_DEV int fx_local_stages_from(int (&re)[8], int (&im)[8], const int2* tw, bool act, TwFn twi) {
+  int scale = 0;
+  if (INV) {
+    const int shift = fx_inverse_shift(re, im, act);
+    scale = shift;
+    if (act) {
+      if (shift == 0) fx_stage_u<0, S0 + T, BIT0 + T>(re, im, tw, twi);
+      else if (shift == 1) fx_stage_u<1, S0 + T, BIT0 + T>(re, im, tw, twi);
+      else fx_stage_u<2, S0 + T, BIT0 + T>(re, im, tw, twi);
+    }
+  } else if (act) {
+    fx_stage_u<-1, S0 + T, BIT0 + T>(re, im, tw, twi);
+  }
+  if (T + 1 < NST) scale += fx_local_stages_from<INV, S0, NST, BIT0, (T + 1 < NST ? T + 1 : T)>(re, im, tw, act, twi);
   return scale;
+}
+template <bool INV, int S0, int NST, int BIT0, typename TwFn>
+NSB_DEV int fx_local_stages_u(int (&re)[8], int (&im)[8], const int2* tw, bool act, TwFn twi) {
+  return fx_local_stages_from<INV, S0, NST, BIT0, 0>(re, im, tw, act, twi);
 }
 
 // Full transform. in: layout A (re/im[r] = point at position 8*lane + r, already in bit-reversed order, i.e.
