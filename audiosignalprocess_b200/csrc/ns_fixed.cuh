@@ -68,8 +68,27 @@ constexpr int kFxTwInt2 = 252;   // filled on the host: nsx_host_init.h nsx_fill
 
 NSB_DEV int fx_swz(int p) { return p ^ ((p >> 3) & 7) ^ (((p >> 6) & 3) << 3); }
 
-NSB_DEV uint32_t fx_pack(int re, int im) { return ((uint32_t)re & 0xffffu) | ((uint32_t)im << 16); }
-NSB_DEV int fx_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+// (re, im) int16 pairs in one word.  On the device each is ONE byte permute (the compiler's own sequences are
+// two instructions for the pack and for the sign-extending low half), on the integer ALU pipe this kernel is
+// bound by; selector 0x9910 = bytes 0, 1 and the sign of byte 1 replicated.
+NSB_DEV uint32_t fx_pack(int re, int im) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(re), "r"(im));
+  return r;
+#else
+  return ((uint32_t)re & 0xffffu) | ((uint32_t)im << 16);
+#endif
+}
+NSB_DEV int fx_lo(uint32_t w) {
+#ifdef __CUDA_ARCH__
+  int r;
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w));
+  return r;
+#else
+  return (int)(int16_t)(w & 0xffffu);
+#endif
+}
 NSB_DEV int fx_hi(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
 // One butterfly on unpacked points a (kept) and x (twiddled), w = (cos, sin).
