@@ -1621,6 +1621,23 @@ __global__ void selftest_kernel(unsigned long long n, unsigned seed, unsigned lo
       const float2 lg = vlog_rn(vadd(mg, make_float2(fabsf(b), 0.25f)));
       if (!same2(lg, nsb_log_rn(__fadd_rn(mg.x, fabsf(b))), nsb_log_rn(__fadd_rn(mg.y, 0.25f)))) ++mism;
     }
+    {
+      // fx_udiv_q20 (ns_fixed.cuh): exact below its bound, never below the reference's cap above it; random
+      // operands of every magnitude, and dividends one below / at / one above an exact multiple of the divisor
+      const unsigned sh1 = (h1 >> 27), sh2 = (h2 >> 27);
+      const unsigned bb = (h2 >> sh2) | 1u;
+      unsigned aa = h1 >> sh1;
+      for (int t = 0; t < 4; ++t) {
+        if (t > 0) {
+          const unsigned long long mlt = (unsigned long long)(h1 % 1200000u) * bb + (unsigned long long)(t - 2) ;
+          if (mlt > 0xffffffffull) continue;
+          aa = (unsigned)mlt;
+          if (t == 1 && aa == 0xffffffffu) continue;
+        }
+        const unsigned want = aa / bb, got = fx_udiv_q20(aa, bb);
+        if (want < kFxUdivExactBelow ? got != want : got < 1048575u) ++mism;
+      }
+    }
     const float c = (float)(h1 % 401u);   // small integers as in counters
     selftest_div(fdiv(c, (float)(h2 % 200u + 1u)), __fdiv_rn(c, (float)(h2 % 200u + 1u)), mism, ulp1, ndiv);
     int32_t v = (int32_t)h2, root = 0;

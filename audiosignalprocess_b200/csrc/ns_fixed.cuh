@@ -33,6 +33,28 @@ NSB_DEV int fx_shift_w32(int x, int c) {  // WEBRTC_SPL_SHIFT_W32
 NSB_DEV int fx_shl(int x, int c) { return (int)((unsigned)x << c); }
 NSB_DEV int fx_mul_rsft_round(int a16, int b16, int c) { return (a16 * b16 + (1 << (c - 1))) >> c; }
 
+// floor(a / b) for b >= 1 when the quotient is below 1 195 000 (1.14 * 2^20); a value of at least 2^20 - 1
+// otherwise.  Every division in the per-bin loops either has a quotient bounded far below that (bounds at the
+// call sites) or is capped at 2^20 - 1 right after, as the reference caps it.  The estimate is a float product
+// built to never exceed the true quotient -- divisor rounded up, reciprocal (1 ulp) scaled by 1 - 2^-22,
+// dividend and product rounded toward zero: between (a/b)(1 - 7 * 2^-23) and a/b -- so its floor is the
+// quotient or one less while a/b < 2^20.19, the remainder a - q b cannot wrap, and one comparison finishes.
+// 9 instructions, four of them conversions / MUFU off the integer pipe, against ~19 for the compiler's general
+// 32-bit division.  Checked on the device against `/` by WebRtcNsB200_SelfTest (random operands and
+// operands placed one below, at and one above exact multiples).
+constexpr unsigned kFxUdivExactBelow = 1195000u;
+NSB_DEV unsigned fx_udiv_q20(unsigned a, unsigned b) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_ru(b)));
+  r = __fmul_rz(r, 0.99999976158142089844f);   // 1 - 2^-22
+  const unsigned q = __float2uint_rz(__fmul_rz(__uint2float_rz(a), r));
+  return a - q * b >= b ? q + 1u : q;
+#else
+  return a / b;
+#endif
+}
+
 // floor(sqrt(v)) for the int32 image of v; 0 when that image is negative,
 // which is what the restoring iteration of SPL/spl_sqrt_floor.c:55 returns.
 NSB_DEV unsigned fx_sqrt_floor(unsigned v) {

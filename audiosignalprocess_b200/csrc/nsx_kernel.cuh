@@ -741,7 +741,7 @@ nsx_process_kernel(const NsxLaunch p) {
           unsigned u1 = magn[j] << 6;
           unsigned u2 = post_shifts < 0 ? (noise[j] >> -post_shifts) : (noise[j] << post_shifts);
           {
-            const unsigned q = (u1 << 11) / (u2 ? u2 : 1u);
+            const unsigned q = fx_udiv_q20(u1 << 11, u2 ? u2 : 1u);   // capped at sat_max below
             const unsigned capped = (u2 && q < sat_max) ? q : sat_max;
             post_snr[j] = u1 > u2 ? capped : 2048u;
           }
@@ -750,7 +750,7 @@ nsx_process_kernel(const NsxLaunch p) {
           u1 = near_est << 3;
           u2 = rb[j].z >> nsh;
           {
-            const unsigned q = u1 / (u2 ? u2 : 1u);
+            const unsigned q = fx_udiv_q20(u1, u2 ? u2 : 1u);   // capped at sat_max below
             prev_near[j] = (u2 && q < sat_max) ? q : sat_max;
           }
           const unsigned prior = prev_near[j] * 2007u + (post_snr[j] - 2048u) * 41u + 512u;
@@ -884,7 +884,8 @@ nsx_process_kernel(const NsxLaunch p) {
           const int nt = fx_norm_u32(post_snr[j]);
           const unsigned num = post_snr[j] << nt;
           const unsigned den = nt > 10 ? (prior_snr[j] << (nt - 11)) : (prior_snr[j] >> (11 - nt));
-          bessel = den ? bessel - (int)(num / (den ? den : 1u)) : 0;
+          // post_snr is in [2048, 2^20), so nt >= 12, den = prior_snr << (nt - 11) >= 2^nt and the quotient < 2^20
+          bessel = den ? bessel - (int)fx_udiv_q20(num, den ? den : 1u) : 0;
           const int zeros = fx_norm_u32(prior_snr[j]);
           int frac32 = (int)(((prior_snr[j] << zeros) & 0x7FFFFFFFu) >> 19);
           int t = (frac32 * frac32 * -43) >> 19;
@@ -990,7 +991,7 @@ nsx_process_kernel(const NsxLaunch p) {
           inv = ((inv >> pre) * (16384 - prior_ns)) >> post;
           const bool live = prior_ns > 0 && lrt[j] < 65300 && nn >= 7;
           const unsigned den = live ? (unsigned)(prior_ns + inv) : 1u;
-          const unsigned q = (unsigned)fx_shl(prior_ns, 8) / den;
+          const unsigned q = fx_udiv_q20((unsigned)fx_shl(prior_ns, 8), den);   // den >= prior_ns: quotient <= 256
           nonspeech[j] = live ? (q & 0xffffu) : 0u;
           rb[j].x = (uint32_t)lrt[j];
         }
@@ -1078,12 +1079,13 @@ nsx_process_kernel(const NsxLaunch p) {
             if (nn > 11) nn = 11;
             u1 <<= nn;
             const unsigned u2 = tn >> (11 - nn);
-            const unsigned q = u2 ? u1 / (u2 ? u2 : 1u) : u1;
+            const unsigned q = u2 ? fx_udiv_q20(u1, u2 ? u2 : 1u) : u1;   // capped at sat_max below
             cur_snr = tm > tn ? (q < sat_max ? q : sat_max) : 0u;
           }
           const unsigned prior = prev_near[j] * 2007u + cur_snr * 41u;
           const unsigned dn = (unsigned)overdrive + ((prior + 8192u) >> 14);
-          const unsigned f16 = ((prior + dn / 2u) / dn) & 0xffffu;
+          // dn = overdrive (>= 256) + ((prior + 8192) >> 14): the quotient stays below 2^14 + 1
+          const unsigned f16 = fx_udiv_q20(prior + dn / 2u, dn) & 0xffffu;
           unsigned flt = f16 > 16384u ? 16384u : (f16 < (unsigned)denoise_bound ? (unsigned)denoise_bound : f16);
           if (block_index < 50) {
             const unsigned u1 = flt * (unsigned)block_index + filter_tmp[j] * (unsigned)(50 - block_index);
