@@ -49,17 +49,25 @@ constexpr int kNsxScratchWords = 256 + 136;          // FFT transposes | time / 
 constexpr int kNsxWarpWords = 2 * kNsxHdrWords + 2 * 129 * 4 + kNsxScratchWords;
 
 NSB_DEV unsigned warp_sum_u(unsigned v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_add_sync(kFullMask, v);   // (ns_warp.cuh: integer warp reductions are one REDUX)
+#else
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
   return v;
+#endif
 }
 NSB_DEV int warp_min_i(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_min_sync(kFullMask, v);
+#else
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const int t = __shfl_xor_sync(kFullMask, v, o);
     v = t < v ? t : v;
   }
   return v;
+#endif
 }
 
 // Q8 log2 of a non-zero magnitude (nsx_core.c:361-367)
@@ -339,7 +347,8 @@ nsx_process_kernel(const NsxLaunch p) {
     int max_int = 0, max_i16 = -1;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      wd[r] = act ? fx_s16(fx_mul_rsft_round(s_win[act ? lane + LANES * r : 0], x[r], 14)) : 0;
+      // (window <= 16384 = Q14 of 1.0 and |x| <= 32768: the rounded product already is an int16, no cast needed)
+      wd[r] = act ? fx_mul_rsft_round(s_win[act ? lane + LANES * r : 0], x[r], 14) : 0;
       const int a = wd[r] < 0 ? -wd[r] : wd[r];
       max_int = a > max_int ? a : max_int;
       const int a16 = wd[r] > 0 ? wd[r] : fx_s16(-wd[r]);  // get_scaling_square.c:33 (int16 negate)
@@ -597,7 +606,7 @@ nsx_process_kernel(const NsxLaunch p) {
           for (int s = 0; s < 3; ++s) {
             // density > 512: delta = FACTOR_Q7 >> (14 - norm16(density)) = 2621440 >> (31 - clz(density))
             const int dv = dn[s] > 513 ? dn[s] : 513;
-            const int delta = dn[s] > 512 ? fx_s16(2621440 >> (31 - __clz(dv))) : dsmall;
+            const int delta = dn[s] > 512 ? 2621440 >> (31 - __clz(dv)) : dsmall;   // shift >= 9: at most 5120
             // delta in [160, 5120] and counter_div in (0, 32767]: 0 <= t16 <= 10240, so the reference's
             // (int16_t) casts of t16 + 1, t16 + 2 and their halves / quarters (exact shifts) are identities
             const int t16 = (delta * cdiv[s]) >> 14;
@@ -606,7 +615,7 @@ nsx_process_kernel(const NsxLaunch p) {
             const int lq_dn = lq_dn0 < logval ? logval : lq_dn0;
             lq[s] = lmagn > lq[s] ? lq_up : lq_dn;
             const int d = fx_s16(lmagn - lq[s]);
-            const int aa = fx_s16(fx_mul_rsft_round(dn[s], cprod[s], 15));
+            const int aa = fx_mul_rsft_round(dn[s], cprod[s], 15);   // two int16 factors: within [-32767, 32766]
             dn[s] = (d >= 0 ? d : -d) < 3 ? fx_s16(aa + bb[s]) : dn[s];
           }
           lqs[j] = sel == 0 ? lq[0] : (sel == 1 ? lq[1] : lq[2]);
@@ -889,7 +898,7 @@ nsx_process_kernel(const NsxLaunch p) {
           const int zeros = fx_norm_u32(prior_snr[j]);
           int frac32 = (int)(((prior_snr[j] << zeros) & 0x7FFFFFFFu) >> 19);
           int t = (frac32 * frac32 * -43) >> 19;
-          t += (fx_s16(frac32) * 5412) >> 12;
+          t += (frac32 * 5412) >> 12;   // frac32 < 2^12
           frac32 = t + 37;
           t = (((31 - zeros) << 12) + frac32) - (11 << 12);
           const int log_t = (t * 178) >> 8;
@@ -981,7 +990,7 @@ nsx_process_kernel(const NsxLaunch p) {
           const int e = (lr * 23637) >> 14;
           int int_part = fx_s16(e >> 12);
           if (int_part < -8) int_part = -8;
-          const int frac = fx_s16(e & 0xfff);
+          const int frac = e & 0xfff;
           int t2 = (frac * frac * 44) >> 19;
           t2 += (frac * 84) >> 7;
           int inv = fx_shl(1, 8 + int_part) + fx_shift_w32(t2, int_part - 4);
@@ -1092,8 +1101,9 @@ nsx_process_kernel(const NsxLaunch p) {
             flt = (u1 / 50u) & 0xffffu;
           }
           // PrepareSpectrum (:455-473)
-          re[j] = fx_s16((re[j] * fx_s16((int)flt)) >> 14);
-          im[j] = fx_s16((im[j] * fx_s16((int)flt)) >> 14);
+          // (flt <= 16384 and the spectrum is int16: the products >> 14 stay within int16, casts not needed)
+          re[j] = (re[j] * (int)flt) >> 14;
+          im[j] = (im[j] * (int)flt) >> 14;
           if (mine) {
             rb[j].z = norm1 > 5 ? noise[j] << (norm1 - 5) : noise[j] >> (5 - norm1);
             rb[j].w = magn[j];
@@ -1173,7 +1183,7 @@ nsx_process_kernel(const NsxLaunch p) {
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const int a = fx_s16(fx_mul_rsft_round(s_win[act ? lane + LANES * r : 0], y[r], 14));
+        const int a = fx_mul_rsft_round(s_win[act ? lane + LANES * r : 0], y[r], 14);   // an int16 already (as above)
         const int t = fx_sat16(fx_mul_rsft_round(a, gain, 13));
         const int prev = r < 3 ? syn_h[r] : 0;
         y[r] = fx_sat16(prev + t);
