@@ -213,27 +213,32 @@ NSB_DEV int fx_local_stages_u(int (&re)[8], int (&im)[8], const int2* tw, bool a
 }
 
 // Full transform. in: layout A (re/im[r] = point at position 8*lane + r, already in bit-reversed order, i.e.
-// position p holds sample bitrev(p)).  out: layout C (point lane + LANES*r).  scr: N words of scratch.
+// position p holds sample bitrev(p)).  out: layout C (point lane + LANES*r).  scr: 2 N words of scratch, 8-byte
+// aligned: the two transposes move (re, im) as one 64-bit word per point -- no packing to int16 pairs and no
+// sign-extending unpack on the integer ALU pipe (24 instructions per transpose and lane), the same number of
+// shared-memory instructions; the XOR swizzle keeps every half-warp of 64-bit accesses on distinct bank pairs
+// (checked per pattern: the low four bits of the swizzled index differ within lanes 0-15 and 16-31).
 template <bool INV, int N>
 NSB_DEV int fx_warp_cfft(int (&re)[8], int (&im)[8], uint32_t* scr, const int2* tw, int lane) {
   constexpr int LANES = N / 8;
   constexpr int STAGES = N == 256 ? 8 : 7;
   const bool act = lane < LANES;
   const int l7 = lane & 7;
+  int2* s2 = reinterpret_cast<int2*>(scr);
   int scale = 0;
   // stages 0-2: t = (r mod 2^s) << (7 - s) = 32 * {0 | 2 (r&1) | r&3}
   scale += fx_local_stages_u<INV, 0, 3, 0>(re, im, tw, act, [&](int s, int r) { return s == 0 ? 0 : (s == 1 ? 2 * (r & 1) : (r & 3)); });
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) scr[fx_swz(8 * lane + r)] = fx_pack(re[r], im[r]);
+    for (int r = 0; r < 8; ++r) s2[fx_swz(8 * lane + r)] = make_int2(re[r], im[r]);
   }
   __syncwarp();
   if (act) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const uint32_t w = scr[fx_swz(l7 + 8 * r + 64 * (lane >> 3))];
-      re[r] = fx_lo(w);
-      im[r] = fx_hi(w);
+      const int2 w = s2[fx_swz(l7 + 8 * r + 64 * (lane >> 3))];
+      re[r] = w.x;
+      im[r] = w.y;
     }
   }
   __syncwarp();
@@ -243,15 +248,15 @@ NSB_DEV int fx_warp_cfft(int (&re)[8], int (&im)[8], uint32_t* scr, const int2* 
   });
   if (act) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) scr[fx_swz(l7 + 8 * r + 64 * (lane >> 3))] = fx_pack(re[r], im[r]);
+    for (int r = 0; r < 8; ++r) s2[fx_swz(l7 + 8 * r + 64 * (lane >> 3))] = make_int2(re[r], im[r]);
   }
   __syncwarp();
   if (act) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const uint32_t w = scr[fx_swz(lane + LANES * r)];
-      re[r] = fx_lo(w);
-      im[r] = fx_hi(w);
+      const int2 w = s2[fx_swz(lane + LANES * r)];
+      re[r] = w.x;
+      im[r] = w.y;
     }
   }
   __syncwarp();

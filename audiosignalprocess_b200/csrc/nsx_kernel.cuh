@@ -37,7 +37,7 @@ constexpr int kNsxWarpsPerCta = 2;        // smallest CTA (and the emulator's)
 #ifndef NSX_MAX_WARPS
 #define NSX_MAX_WARPS 28
 #endif
-constexpr int kNsxMaxWarpsPerCta = NSX_MAX_WARPS;    // 72 registers x 896 threads, 168 KB of shared memory
+constexpr int kNsxMaxWarpsPerCta = NSX_MAX_WARPS;    // 72 registers x 896 threads, 196 KB of shared memory
 #ifndef NSX_FRAME_SYNC
 #define NSX_FRAME_SYNC 1
 #endif
@@ -45,7 +45,7 @@ constexpr int kNsxMaxWarpsPerCta = NSX_MAX_WARPS;    // 72 registers x 896 threa
 // (one for the tables, two per warp: header + sample histories | per-bin records)
 constexpr int kNsxCtaBarWords = (2 * (1 + 2 * kNsxMaxWarpsPerCta) + 3) / 4 * 4;
 constexpr int kNsxCtaTableWords = kNsxTableImgWords + kNsxCtaBarWords;
-constexpr int kNsxScratchWords = 256 + 136;          // FFT transposes | time / spectrum buffer
+constexpr int kNsxScratchWords = 512 + 136;          // FFT transposes (64-bit points) | time / spectrum buffer
 constexpr int kNsxWarpWords = 2 * kNsxHdrWords + 2 * 129 * 4 + kNsxScratchWords;
 
 NSB_DEV unsigned warp_sum_u(unsigned v) {
@@ -229,8 +229,8 @@ nsx_process_kernel(const NsxLaunch p) {
   int* Hw = reinterpret_cast<int*>(W + kNsxHdrWords);
   uint4* RA = reinterpret_cast<uint4*>(W + 2 * kNsxHdrWords);
   uint4* RB = RA + 129;
-  uint32_t* scr = reinterpret_cast<uint32_t*>(RB + 129);  // 256 words: FFT transposes
-  uint32_t* buf = scr + 256;                              // 136 words: time / spectrum staging
+  uint32_t* scr = reinterpret_cast<uint32_t*>(RB + 129);  // 512 words: FFT transposes
+  uint32_t* buf = scr + 512;                              // 136 words: time / spectrum staging
 
   // ---- tables and state: HBM -> shared by TMA bulk copies issued by one lane (see nsf_kernel.cuh);
   // the sample histories pass through the FFT scratch on their way to registers
