@@ -189,6 +189,8 @@ def main():
     for fs in (8000, 16000, 32000, 48000):
         cases.append(("%d streams x %d s, fs=%d mode=2" % (bn, bf // 100, fs), fs, 2, bn, bf if fs <= 16000 else bf // 2,
                       4242, fs <= 16000, [100]))
+    for mode in (0, 1, 3):   # the other policies at the headline rate
+        cases.append(("%d streams x %d s, fs=16000 mode=%d" % (bn, bf // 100, mode), 16000, mode, bn, bf, 4242 + mode, True, [100]))
     rows, triage_rows = [], []
     budget = a.triage
     for name, fs, mode, n, frames, seed, want_float, chunks in cases:
